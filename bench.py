@@ -1,0 +1,422 @@
+#!/usr/bin/env python3
+"""bench.py - frames/s of the B200-native bayer2rgb hot path (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = ONE pass of the hot path over one batch of synthetic frames resident in HBM
+(3840x2160 bggr -> RGBA; the batch is far larger than the 126 MB L2, so no launch is served
+from cache). N = 1: one batched launch of b200vf_bayer2rgb per step (whole frames, TMA kernel).
+N > 1: every frame is row-sharded over the N ranks (one process per GPU); a step is the packed
+NCCL halo exchange of the mosaic's boundary rows + b200vf_bayer2rgb_shard on N x the frames,
+so per-GPU work stays fixed (weak scaling). Timed on the device with CUDA events on the
+launching stream, barrier + synchronize on both sides, max over ranks.
+
+`value` has inputs already in HBM; `e2e` is the same metric through the element mirror's
+transform vfunc on pinned HOST buffers (H2D + kernel + D2H inside the timed region).
+`roofline` is the bayer2rgb kernel's algorithmic bytes (5 B/px) per launch over
+its launch duration, against the measured HBM peak of MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference` time the reference's own C inner loops (oracle/_ref,
+compiled from /root/reference; ORC C backup, not the ORC JIT) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "gst-plugins-bad_b200"))
+
+W4K, H4K = 3840, 2160
+METRIC = "bayer2rgb frames/s (3840x2160 bggr->RGBA)"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+# ------------------------------------------------------------------------- CPU reference
+def cpu_reference(seconds, threads, frames_per_call=1):
+    """Times the reference's CPU path (oracle/_ref when built, else the port) on 4K bggr->RGBA frames.
+    The ONLY place bench.py executes anything under oracle/ - as the baseline, never as the product."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    orc = oracle.best()
+    rng = np.random.default_rng(0)
+    srcs = [rng.integers(0, 256, (H4K, W4K), dtype=np.uint8) for _ in range(threads)]
+    done = [0] * threads
+    stop = time.perf_counter() + seconds
+
+    def work(i):
+        while True:
+            for _ in range(frames_per_call):
+                orc.bayer2rgb(srcs[i], W4K, H4K, "bggr", "RGBA")      # ctypes call: the GIL is released inside
+            done[i] += frames_per_call
+            if time.perf_counter() >= stop:
+                return
+
+    orc.bayer2rgb(srcs[0], W4K, H4K, "bggr", "RGBA")                  # warm-up
+    t0 = time.perf_counter()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    dt = time.perf_counter() - t0
+    return sum(done) / dt, sum(done), dt, orc.kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    per_step = 2 * cores                                               # frames per step (2 per thread)
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    orc = oracle.best()
+    rng = np.random.default_rng(0)
+    srcs = [rng.integers(0, 256, (H4K, W4K), dtype=np.uint8) for _ in range(cores)]
+
+    def step():
+        def work(i):
+            for _ in range(per_step // cores):
+                orc.bayer2rgb(srcs[i], W4K, H4K, "bggr", "RGBA")
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step()
+    steps = min(args.steps, 40)                                       # bounded: each step is ~2 frames of CPU work per core
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    fps = per_step * steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "bayer2rgb 3840x2160 bggr->RGBA", "frames_per_step": per_step,
+                   "note": "reference CPU inner loops (gstbayer2rgb.c:354-451 + ORC C backup, not the ORC JIT), all host threads"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": orc.kind,
+                         "sample": "%d steps x %d 4K frames on %d threads" % (steps, per_step, cores)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,utilization.gpu,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        clk, mx, reasons = [], 0, set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm, smax, util = float(f[1]), float(f[2]), float(f[3])
+            except ValueError:
+                continue
+            mx = max(mx, smax)
+            if util >= 50:                                            # under load only
+                clk.append(sm)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        clk.sort()
+        return {"sm_mhz": clk[len(clk) // 2] if clk else None, "sm_max_mhz": mx or None, "samples_under_load": len(clk),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--frames", type=int, default=384, help="4K frames resident per GPU per step")
+    ap.add_argument("--no-elements", action="store_true", help="skip the per-element side measurements")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import b200vf                                                      # raises if libb200vf.so is missing: no fallback
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warmup = max(args.warmup, 3)
+    ctx = b200vf.Context(local)
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    st = side.cuda_stream
+    w, h, B = W4K, H4K, args.frames
+    peak, peak_kind = hbm_peak()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234 + rank)
+
+    comm = None
+    if world == 1:
+        src = torch.randint(0, 256, (B, h, w), dtype=torch.uint8, device="cuda", generator=gen)
+        dst = torch.empty((B, h, 4 * w), dtype=torch.uint8, device="cuda")
+        nfr = B
+
+        def step():
+            ctx.bayer2rgb(src, w, dst, 4 * w, w, h, 0, (0, 1, 2), nframes=B, stream=st)
+        parallelism = "1 GPU, whole frames"
+    else:
+        # row shards of N*B frames: [halo row | shard rows | halo row] per frame
+        r0, rows = b200vf.shard_rows(h, rank, world)
+        nfr = B * world
+        fs = (rows + 2) * w
+        src = torch.randint(0, 256, (nfr, rows + 2, w), dtype=torch.uint8, device="cuda", generator=gen)
+        dst = torch.empty((nfr, rows, 4 * w), dtype=torch.uint8, device="cuda")
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            import ctypes
+            buf = (ctypes.c_uint8 * 128)()
+            b200vf.check(b200vf.lib.b200vf_comm_unique_id(buf))
+            idt = torch.tensor(list(buf), dtype=torch.uint8)
+        idt = idt.cuda()
+        dist.broadcast(idt, 0)
+        import ctypes
+        idb = (ctypes.c_uint8 * 128)(*idt.cpu().tolist())
+        ch = ctypes.c_void_p()
+        b200vf.check(b200vf.lib.b200vf_comm_create(ctx.h, idb, rank, world, ctypes.byref(ch)))
+        comm = ch
+
+        def step():
+            b200vf.check(b200vf.lib.b200vf_comm_halo_exchange(comm, src.data_ptr(), w, rows, 1, fs, nfr, st))
+            ctx.bayer2rgb_shard(src.data_ptr() + w, w, dst, 4 * w, w, h, r0, rows, 0, (0, 1, 2), nframes=nfr,
+                                src_frame_stride=fs, dst_frame_stride=rows * 4 * w, stream=st)
+        parallelism = "%d GPUs, every frame row-sharded (rows %d..%d on rank %d), packed NCCL halo exchange of 1 mosaic row" % (
+            world, r0, r0 + rows, rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(warmup):
+        step()
+    barrier()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(side)
+    for _ in range(args.steps):
+        step()
+    e1.record(side)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    # keep the GPU under the same load a little longer so the 50 ms clock sampler sees it (untimed)
+    t_probe = time.perf_counter()
+    while time.perf_counter() - t_probe < 1.0 and rank == 0:
+        step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    ms_per_step = ms / args.steps
+    fps = nfr * args.steps / (ms * 1e-3)
+
+    # ---- e2e: the element's transform vfunc on pinned host buffers (H2D + kernel + D2H timed)
+    Be = 16
+    el = ctx.element("bayer2rgb")
+    el.set_caps("bggr", "RGBA", w, h)
+    import ctypes
+    hin, hout = ctypes.c_void_p(), ctypes.c_void_p()
+    b200vf.check(b200vf.lib.b200vf_host_alloc(Be * w * h, ctypes.byref(hin)))
+    b200vf.check(b200vf.lib.b200vf_host_alloc(Be * w * h * 4, ctypes.byref(hout)))
+    np.ctypeslib.as_array(ctypes.cast(hin, ctypes.POINTER(ctypes.c_uint8)), shape=(Be * w * h,))[:] = \
+        np.random.default_rng(rank).integers(0, 256, Be * w * h, dtype=np.uint8)
+    for _ in range(2):
+        el.transform_host_ptr(hin, hout, Be)
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        el.transform_host_ptr(hin, hout, Be)                          # synchronous: returns when the last D2H landed
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_fps = Be * world * e2e_steps / float(tt.item())
+    b200vf.lib.b200vf_host_free(hin)
+    b200vf.lib.b200vf_host_free(hout)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # one launch moves nfr * w*h * 5 algorithmic bytes on this GPU's share
+    px_per_launch = (nfr // world) * w * h if world > 1 else nfr * w * h
+    kernel_ms = ms_per_step                                            # N=1: the step IS the launch (CUDA events around it)
+    achieved = px_per_launch * 5 / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "bayer2rgb 3840x2160 bggr->RGBA (BASELINE.json configs[1])", "frames_per_step": nfr,
+                   "parallelism": parallelism, "kernel": ctx.last_kernel(),
+                   "l2": "inputs+outputs per step = %.1f GB per GPU, far larger than L2 (no flush needed)" % (
+                       px_per_launch * 5 / 1e9)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_kind": peak_kind,
+                     "note": "5 algorithmic B/px x pixels per launch / CUDA-event launch time; at N>1 the step also "
+                             "contains the halo exchange"},
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": Be * w * h * world,
+                "d2h_bytes_per_step": Be * w * h * 4 * world,
+                "note": "b200vf_element_transform_host: pinned host in/out, 3-stream H2D/kernel/D2H pipeline, %d frames per step per GPU" % Be},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if world == 1:
+        fps_cpu, n_cpu, dt_cpu, kind = cpu_reference(8.0, 1)
+        line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": 1, "kind": kind,
+                                "sample": "%d 4K frames in %.1f s, 1 thread (the element runs on one streaming thread); "
+                                          "ORC C backup, not the ORC JIT" % (n_cpu, dt_cpu)}
+        if not args.no_elements:
+            try:
+                line["elements"] = side_measurements(ctx, torch, b200vf, st, side, peak)
+            except Exception as ex:                                    # side numbers must never sink the headline
+                line["elements"] = {"error": str(ex)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def side_measurements(ctx, torch, b200vf, st, side, peak):
+    """Frames/s and % of the HBM roofline of the other elements of the hot path (untimed extras,
+    same methodology: device-resident batches larger than L2, CUDA events, 3 warm-ups)."""
+    import numpy as np
+    out = {}
+
+    def timeit(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(side)
+        for _ in range(iters):
+            fn()
+        b.record(side)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters * 1e-3
+
+    def rec(name, n, px, bpp, t, extra=None):
+        gbs = n * px * bpp / t / 1e9
+        d = {"fps": n / t, "GBps": gbs, "frac_hbm": gbs / peak, "frames": n, "kernel": ctx.last_kernel()}
+        if extra:
+            d.update(extra)
+        out[name] = d
+
+    for (w, h, tag) in [(3840, 2160, "4k"), (7680, 4320, "8k")]:
+        px = w * h
+        n = max(4, int(3e9 // (px * 5)))
+        src = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, device="cuda")
+        dst = torch.empty((n, h, 4 * w), dtype=torch.uint8, device="cuda")
+        for var in ("tma", "direct"):
+            ctx.set_variant(var)
+            t = timeit(lambda: ctx.bayer2rgb(src, w, dst, 4 * w, w, h, 0, (0, 1, 2), nframes=n, stream=st))
+            rec("bayer2rgb_%s_%s" % (tag, var), n, px, 5, t)
+        ctx.set_variant("auto")
+        if tag == "8k":
+            # BASELINE.json configs[4]: bayer2rgb ! coloreffects(sepia) ! solarize, fused vs per-element launches
+            table, ml = b200vf.coloreffects_table(2)
+            sol = b200vf.lut_solarize()
+            t = timeit(lambda: ctx.bayer2rgb_fused(src, w, dst, 4 * w, w, h, 0, (0, 1, 2), luma_table=table, lut=sol,
+                                                   nframes=n, stream=st))
+            rec("chain_8k_fused", n, px, 5, t)
+
+            def unfused():
+                ctx.bayer2rgb(src, w, dst, 4 * w, w, h, 0, (0, 1, 2), nframes=n, stream=st)
+                ctx.coloreffects_rgb(dst, w, h, 4 * w, 4, (0, 1, 2), table, ml, nframes=n, stream=st)
+                ctx.lut4(dst, dst, n * px, sol, stream=st)
+            t = timeit(unfused)
+            rec("chain_8k_unfused", n, px, 21, t, {"launches_per_frame_batch": 3})
+        del src
+        # 4-byte -> 4-byte elements on the RGBA batch
+        n4 = max(2, min(n, int(3e9 // (px * 8))))
+        a = dst[:n4]
+        b = torch.empty_like(a)
+        t = timeit(lambda: ctx.lut4(a, b, n4 * px, b200vf.lut_burn(175), stream=st))
+        rec("burn_lut4_%s" % tag, n4, px, 8, t)
+        t = timeit(lambda: ctx.exclusion(a, b, n4 * px, 175, stream=st))
+        rec("exclusion_%s" % tag, n4, px, 8, t)
+        t = timeit(lambda: ctx.dilate(a, b, w, h, False, nframes=n4, stream=st))
+        rec("dilate_%s" % tag, n4, px, 8, t)
+        table, ml = b200vf.coloreffects_table(2)
+        t = timeit(lambda: ctx.coloreffects_rgb(b, w, h, 4 * w, 4, (0, 1, 2), table, ml, nframes=n4, stream=st))
+        rec("coloreffects_sepia_%s" % tag, n4, px, 8, t)
+        t = timeit(lambda: ctx.chromahold(b, w, h, 4 * w, (0, 1, 2), (255, 0, 0), 30, nframes=n4, stream=st))
+        rec("chromahold_%s" % tag, n4, px, 8, t)
+        # gaussianblur sigma=5 (27 taps): FP32-issue bound; report vs both rooflines
+        k, ks = b200vf.gauss_kernel(5.0)
+        ng = 4
+        for exact in (1, 0):
+            t = timeit(lambda: ctx.gaussblur(a, b, w, h, 4 * w, 1, k, ks, exact=bool(exact), nframes=ng, stream=st), iters=3)
+            flops = 16 * len(k) * px * ng
+            rec("gaussblur_sigma5_%s_%s" % (tag, "exact" if exact else "fma"), ng, px, 8, t,
+                {"fp32_ops_per_s": flops / t, "bound": "fp32 issue, not HBM (SURVEY D6)"})
+        if tag == "8k":
+            # BASELINE.json configs[3]: fisheye 7680x4320 RGBA (nearest-neighbour gather, index table)
+            t0 = time.perf_counter()
+            m = b200vf.gt_build_map("fisheye", w, h)
+            idx = b200vf.gt_resolve_map(m, w, h, 1)
+            t_map = time.perf_counter() - t0
+            d_idx = torch.from_numpy(idx).cuda()
+            t = timeit(lambda: ctx.remap(a, b, d_idx, w, h, 4, 4 * w, nframes=n4, stream=st))
+            rec("fisheye_8k_remap", n4, px, 8, t, {"host_map_build_s": t_map, "index_table_bytes_per_px": 4})
+        del a, b, dst
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,414 @@
+"""ctypes binding of libb200vf.so (include/b200vf.h).
+
+Thin by design: every call below is one C-ABI call; the product is the shared
+library.  Import fails loudly when the library has not been built, and
+`Context()` fails loudly when there is no sm_100 GPU - there is no CPU path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "..", "lib", "libb200vf.so")
+
+
+class B200vfError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("b200vf status %d: %s" % (status, message))
+        self.status = status
+
+
+OK, E_INVAL, E_NO_DEVICE, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_NOT_NEGOTIATED, E_NCCL, E_PROPERTY = 0, -1, -2, -3, -4, -5, -6, -7, -8
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("libb200vf.so is not built (%s); run `make -C gst-plugins-bad_b200/csrc` or "
+                      "__graft_entry__.build() - the CUDA extension is mandatory, there is no fallback" % LIB_PATH)
+lib = C.CDLL(os.path.abspath(LIB_PATH))
+
+_vp, _i, _sz, _u32 = C.c_void_p, C.c_int, C.c_size_t, C.c_uint32
+_LUT = C.c_uint8 * 1024
+
+_SIGS = {
+    "b200vf_version": (_i, []),
+    "b200vf_last_error": (C.c_char_p, []),
+    "b200vf_status_string": (C.c_char_p, [_i]),
+    "b200vf_ctx_create": (_i, [_i, C.POINTER(_vp)]),
+    "b200vf_ctx_destroy": (None, [_vp]),
+    "b200vf_ctx_device": (_i, [_vp]),
+    "b200vf_ctx_stream": (_vp, [_vp]),
+    "b200vf_ctx_sm_count": (_i, [_vp]),
+    "b200vf_ctx_synchronize": (_i, [_vp, _vp]),
+    "b200vf_ctx_launch_count": (C.c_uint64, [_vp]),
+    "b200vf_ctx_last_kernel": (C.c_char_p, [_vp]),
+    "b200vf_ctx_set_variant": (_i, [_vp, _i]),
+    "b200vf_pool_create": (_i, [_vp, _sz, _i, C.POINTER(_vp)]),
+    "b200vf_pool_destroy": (None, [_vp]),
+    "b200vf_pool_acquire": (_i, [_vp, C.POINTER(_i)]),
+    "b200vf_pool_release": (_i, [_vp, _i]),
+    "b200vf_pool_device_ptr": (_vp, [_vp, _i]),
+    "b200vf_pool_host_ptr": (_vp, [_vp, _i]),
+    "b200vf_pool_buf_bytes": (_sz, [_vp]),
+    "b200vf_pool_buf_pitch": (_sz, [_vp]),
+    "b200vf_pool_upload": (_i, [_vp, _i, _vp, _sz, _vp]),
+    "b200vf_pool_download": (_i, [_vp, _i, _vp, _sz, _vp]),
+    "b200vf_malloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
+    "b200vf_free": (_i, [_vp, _vp]),
+    "b200vf_host_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "b200vf_host_free": (_i, [_vp]),
+    "b200vf_memcpy_h2d": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "b200vf_memcpy_d2h": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "b200vf_bayer2rgb": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200vf_bayer2rgb_shard": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200vf_rgb2bayer": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _vp]),
+    "b200vf_lut4": (_i, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "b200vf_lut_burn": (_i, [_i, _vp]),
+    "b200vf_lut_dodge": (_i, [_vp]),
+    "b200vf_lut_chromium": (_i, [_i, _i, _vp]),
+    "b200vf_lut_solarize": (_i, [_i, _i, _i, _vp]),
+    "b200vf_lut_compose": (_i, [_vp, _vp, _vp]),
+    "b200vf_exclusion": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
+    "b200vf_dilate": (_i, [_vp, _vp, _vp, _i, _i, _sz, _i, _i, _vp, _vp]),
+    "b200vf_gauss_kernel": (_i, [C.c_float, _vp, _vp, _i]),
+    "b200vf_gaussblur": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _sz, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "b200vf_coloreffects_table": (_i, [_i, C.POINTER(_vp), C.POINTER(_i)]),
+    "b200vf_coloreffects_rgb": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "b200vf_coloreffects_ayuv": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _i, _i, _vp, _i, _vp]),
+    "b200vf_chromahold": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200vf_gt_build_map": (_i, [C.c_char_p, _i, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_double), _i, _vp]),
+    "b200vf_gt_resolve_map": (_i, [_vp, _i, _i, _i, _vp]),
+    "b200vf_remap": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _sz, _i, _u32, _vp]),
+    "b200vf_bayer2rgb_fused": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "b200vf_comm_unique_id": (_i, [_vp]),
+    "b200vf_comm_create": (_i, [_vp, _vp, _i, _i, C.POINTER(_vp)]),
+    "b200vf_comm_destroy": (None, [_vp]),
+    "b200vf_shard_rows": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "b200vf_comm_halo_exchange": (_i, [_vp, _vp, _sz, _i, _i, _sz, _i, _vp]),
+    "b200vf_comm_barrier": (_i, [_vp, _vp]),
+    "b200vf_element_factory_make": (_i, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "b200vf_element_destroy": (None, [_vp]),
+    "b200vf_element_factory_name": (C.c_char_p, [_vp]),
+    "b200vf_element_set_property": (_i, [_vp, C.c_char_p, C.c_double]),
+    "b200vf_element_set_property_string": (_i, [_vp, C.c_char_p, C.c_char_p]),
+    "b200vf_element_get_property": (_i, [_vp, C.c_char_p, C.POINTER(C.c_double)]),
+    "b200vf_element_set_caps": (_i, [_vp, C.c_char_p, C.c_char_p, _i, _i]),
+    "b200vf_element_unit_size": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
+    "b200vf_element_transform_host": (_i, [_vp, _vp, _vp, _i]),
+    "b200vf_element_transform_device": (_i, [_vp, _vp, _vp, _i, _vp]),
+}
+
+MISSING = []
+for _name, (_res, _args) in _SIGS.items():
+    try:
+        _f = getattr(lib, _name)
+    except AttributeError:
+        MISSING.append(_name)
+        continue
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+def declared_symbols():
+    return sorted(_SIGS)
+
+
+def check(status):
+    if status != OK:
+        raise B200vfError(status, lib.b200vf_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(x):
+    """Device pointer from a DeviceBuffer, an int, or anything with data_ptr() (torch tensors)."""
+    if x is None:
+        return None
+    if isinstance(x, DeviceBuffer):
+        return x.ptr
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    return int(x)
+
+
+def _hptr(a):
+    return a.ctypes.data_as(_vp) if isinstance(a, np.ndarray) else a
+
+
+def _lut_arg(lut):
+    if lut is None:
+        return None
+    a = np.ascontiguousarray(lut, dtype=np.uint8)
+    assert a.shape == (4, 256), a.shape
+    return a
+
+
+class Context:
+    def __init__(self, device=0):
+        h = _vp()
+        check(lib.b200vf_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib.b200vf_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return lib.b200vf_ctx_stream(self.h)
+
+    @property
+    def sm_count(self):
+        return lib.b200vf_ctx_sm_count(self.h)
+
+    def synchronize(self, stream=None):
+        check(lib.b200vf_ctx_synchronize(self.h, stream))
+
+    def launch_count(self):
+        return int(lib.b200vf_ctx_launch_count(self.h))
+
+    def last_kernel(self):
+        return lib.b200vf_ctx_last_kernel(self.h).decode()
+
+    def set_variant(self, v):
+        check(lib.b200vf_ctx_set_variant(self.h, {"auto": 0, "direct": 1, "tma": 2}.get(v, v)))
+
+    # -- memory -----------------------------------------------------------
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def upload(self, array, stream=None):
+        a = np.ascontiguousarray(array)
+        b = DeviceBuffer(self, a.nbytes)
+        check(lib.b200vf_memcpy_h2d(self.h, b.ptr, _hptr(a), a.nbytes, stream))
+        self.synchronize(stream)
+        return b
+
+    def download(self, buf, nbytes=None, dtype=np.uint8, stream=None, offset=0):
+        n = nbytes if nbytes is not None else buf.nbytes - offset
+        out = np.empty(n, np.uint8)
+        check(lib.b200vf_memcpy_d2h(self.h, _hptr(out), _ptr(buf) + offset, n, stream))
+        self.synchronize(stream)
+        return out.view(dtype)
+
+    # -- ops (device pointers) ----------------------------------------------
+    def bayer2rgb(self, src, src_stride, dst, dst_stride, width, height, pattern, offs, nframes=1,
+                  src_frame_stride=None, dst_frame_stride=None, stream=None):
+        sfs = src_frame_stride if src_frame_stride is not None else src_stride * height
+        dfs = dst_frame_stride if dst_frame_stride is not None else dst_stride * height
+        check(lib.b200vf_bayer2rgb(self.h, _ptr(src), src_stride, sfs, _ptr(dst), dst_stride, dfs, width, height,
+                                   nframes, pattern, offs[0], offs[1], offs[2], stream))
+
+    def bayer2rgb_shard(self, src, src_stride, dst, dst_stride, width, full_height, row0, rows, pattern, offs,
+                        nframes=1, src_frame_stride=0, dst_frame_stride=0, stream=None):
+        check(lib.b200vf_bayer2rgb_shard(self.h, _ptr(src), src_stride, src_frame_stride, _ptr(dst), dst_stride,
+                                         dst_frame_stride, width, full_height, row0, rows, nframes, pattern,
+                                         offs[0], offs[1], offs[2], stream))
+
+    def bayer2rgb_fused(self, src, src_stride, dst, dst_stride, width, height, pattern, offs, luma_table=None,
+                        lut=None, nframes=1, src_frame_stride=None, dst_frame_stride=None, stream=None):
+        sfs = src_frame_stride if src_frame_stride is not None else src_stride * height
+        dfs = dst_frame_stride if dst_frame_stride is not None else dst_stride * height
+        lt = None if luma_table is None else np.ascontiguousarray(luma_table, np.uint8)
+        la = _lut_arg(lut)
+        check(lib.b200vf_bayer2rgb_fused(self.h, _ptr(src), src_stride, sfs, _ptr(dst), dst_stride, dfs, width,
+                                         height, nframes, pattern, offs[0], offs[1], offs[2],
+                                         None if lt is None else _hptr(lt), None if la is None else _hptr(la), stream))
+
+    def rgb2bayer(self, src, src_stride, dst, dst_stride, width, height, pattern, nframes=1, stream=None):
+        check(lib.b200vf_rgb2bayer(self.h, _ptr(src), src_stride, src_stride * height, _ptr(dst), dst_stride,
+                                   dst_stride * height, width, height, nframes, pattern, stream))
+
+    def lut4(self, src, dst, npix, lut, stream=None):
+        la = _lut_arg(lut)
+        check(lib.b200vf_lut4(self.h, _ptr(src), _ptr(dst), npix, _hptr(la), stream))
+
+    def exclusion(self, src, dst, npix, factor, stream=None):
+        check(lib.b200vf_exclusion(self.h, _ptr(src), _ptr(dst), npix, factor, stream))
+
+    def dilate(self, src, dst, width, height, erode=False, nframes=1, below=None, stream=None):
+        check(lib.b200vf_dilate(self.h, _ptr(src), _ptr(dst), width, height, 4 * width * height, nframes,
+                                int(bool(erode)), _ptr(below), stream))
+
+    def gaussblur(self, src, dst, width, height, stride, p0, kernel, kernel_sum, exact=True, nframes=1,
+                  frame_stride=None, row0=0, rows=None, full_height=None, stream=None):
+        k = np.ascontiguousarray(kernel, np.float32)
+        ks = np.ascontiguousarray(kernel_sum, np.float32)
+        fh = full_height if full_height is not None else height
+        rws = rows if rows is not None else height
+        fs = frame_stride if frame_stride is not None else stride * rws
+        check(lib.b200vf_gaussblur(self.h, _ptr(src), _ptr(dst), width, fh, row0, rws, stride, fs, nframes, p0,
+                                   _hptr(k), _hptr(ks), len(k), int(bool(exact)), stream))
+
+    def coloreffects_rgb(self, data, width, height, row_stride, pixel_stride, offs, table, map_luma, nframes=1,
+                         stream=None):
+        t = np.ascontiguousarray(table, np.uint8)
+        check(lib.b200vf_coloreffects_rgb(self.h, _ptr(data), width, height, row_stride, row_stride * height, nframes,
+                                          pixel_stride, offs[0], offs[1], offs[2], _hptr(t), int(map_luma), stream))
+
+    def coloreffects_ayuv(self, data, width, height, row_stride, offs, table, map_luma, nframes=1, stream=None):
+        t = np.ascontiguousarray(table, np.uint8)
+        check(lib.b200vf_coloreffects_ayuv(self.h, _ptr(data), width, height, row_stride, row_stride * height, nframes,
+                                           offs[0], offs[1], offs[2], _hptr(t), int(map_luma), stream))
+
+    def chromahold(self, data, width, height, row_stride, offs, target, tolerance, nframes=1, stream=None):
+        check(lib.b200vf_chromahold(self.h, _ptr(data), width, height, row_stride, row_stride * height, nframes,
+                                    offs[0], offs[1], offs[2], target[0], target[1], target[2], tolerance, stream))
+
+    def remap(self, src, dst, index, width, height, pixel_stride, row_stride, fill=0, nframes=1, stream=None):
+        check(lib.b200vf_remap(self.h, _ptr(src), _ptr(dst), _ptr(index), width, height, pixel_stride, row_stride,
+                               row_stride * height, nframes, fill, stream))
+
+    def element(self, factory):
+        return Element(self, factory)
+
+
+class DeviceBuffer:
+    def __init__(self, ctx, nbytes):
+        p = _vp()
+        check(lib.b200vf_malloc(ctx.h, nbytes, C.byref(p)))
+        self.ctx, self.ptr, self.nbytes = ctx, p.value, nbytes
+
+    def free(self):
+        if self.ptr and self.ctx.h:
+            lib.b200vf_free(self.ctx.h, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------- host helpers
+def lut_burn(adjustment=175):
+    a = np.zeros((4, 256), np.uint8)
+    check(lib.b200vf_lut_burn(adjustment, _hptr(a)))
+    return a
+
+
+def lut_dodge():
+    a = np.zeros((4, 256), np.uint8)
+    check(lib.b200vf_lut_dodge(_hptr(a)))
+    return a
+
+
+def lut_chromium(edge_a=200, edge_b=1):
+    a = np.zeros((4, 256), np.uint8)
+    check(lib.b200vf_lut_chromium(edge_a, edge_b, _hptr(a)))
+    return a
+
+
+def lut_solarize(threshold=127, start=50, end=185):
+    a = np.zeros((4, 256), np.uint8)
+    check(lib.b200vf_lut_solarize(threshold, start, end, _hptr(a)))
+    return a
+
+
+def lut_compose(first, second):
+    a = np.zeros((4, 256), np.uint8)
+    f, s = _lut_arg(first), _lut_arg(second)
+    check(lib.b200vf_lut_compose(_hptr(f), _hptr(s), _hptr(a)))
+    return a
+
+
+def gauss_kernel(sigma):
+    k = np.zeros(128, np.float32)
+    s = np.zeros(128, np.float32)
+    ws = lib.b200vf_gauss_kernel(C.c_float(sigma), _hptr(k), _hptr(s), 128)
+    if ws < 0:
+        check(ws)
+    return k[:ws].copy(), s[:ws].copy()
+
+
+def coloreffects_table(preset):
+    """preset: 1 heat, 2 sepia, 3 xray, 4 xpro, 5 yellowblue -> (uint8[768], map_luma)"""
+    p = _vp()
+    ml = _i(0)
+    check(lib.b200vf_coloreffects_table(preset, C.byref(p), C.byref(ml)))
+    arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(768,)).copy()
+    return arr, ml.value
+
+
+def gt_build_map(element, width, height, props=None):
+    props = props or {}
+    names = [k.replace("_", "-").encode() for k in props]
+    n = len(names)
+    cn = (C.c_char_p * max(n, 1))(*names)
+    cv = (C.c_double * max(n, 1))(*[float(v) for v in props.values()])
+    m = np.zeros((height, width, 2), np.float64)
+    check(lib.b200vf_gt_build_map(element.encode(), width, height, cn, cv, n, _hptr(m)))
+    return m
+
+
+def gt_resolve_map(map_xy, width, height, off_edge):
+    idx = np.zeros((height, width), np.int32)
+    m = np.ascontiguousarray(map_xy, np.float64)
+    check(lib.b200vf_gt_resolve_map(_hptr(m), width, height, off_edge, _hptr(idx)))
+    return idx
+
+
+def shard_rows(height, rank, nranks):
+    r0, r = _i(0), _i(0)
+    check(lib.b200vf_shard_rows(height, rank, nranks, C.byref(r0), C.byref(r)))
+    return r0.value, r.value
+
+
+class Element:
+    """Mirror of a reference element: factory name, properties, caps, transform."""
+
+    def __init__(self, ctx, factory):
+        h = _vp()
+        check(lib.b200vf_element_factory_make(ctx.h, factory.encode(), C.byref(h)))
+        self.h, self.ctx, self.factory = h, ctx, factory
+
+    def close(self):
+        if self.h:
+            lib.b200vf_element_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_property(self, name, value):
+        if isinstance(value, str):
+            check(lib.b200vf_element_set_property_string(self.h, name.encode(), value.encode()))
+        else:
+            check(lib.b200vf_element_set_property(self.h, name.encode(), float(value)))
+
+    def get_property(self, name):
+        v = C.c_double(0)
+        check(lib.b200vf_element_get_property(self.h, name.encode(), C.byref(v)))
+        return v.value
+
+    def set_caps(self, in_format, out_format, width, height):
+        check(lib.b200vf_element_set_caps(self.h, in_format.encode(), (out_format or in_format).encode(), width, height))
+
+    def unit_size(self):
+        a, b = _sz(0), _sz(0)
+        check(lib.b200vf_element_unit_size(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def transform(self, frames_in, nframes=1):
+        """Host path: numpy in -> numpy out (upload, kernel, download inside)."""
+        a = np.ascontiguousarray(frames_in, np.uint8)
+        in_b, out_b = self.unit_size()
+        assert a.nbytes == in_b * nframes, (a.nbytes, in_b, nframes)
+        out = np.empty(out_b * nframes, np.uint8)
+        check(lib.b200vf_element_transform_host(self.h, _hptr(a), _hptr(out), nframes))
+        return out
+
+    def transform_host_ptr(self, h_in, h_out, nframes):
+        check(lib.b200vf_element_transform_host(self.h, h_in, h_out, nframes))
+
+    def transform_device(self, d_in, d_out, nframes=1, stream=None):
+        check(lib.b200vf_element_transform_device(self.h, _ptr(d_in), _ptr(d_out), nframes, stream))

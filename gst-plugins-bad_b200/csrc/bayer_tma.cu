@@ -1,0 +1,258 @@
+// bayer_tma.cu - bayer2rgb fed by TMA 2-D tiles (the sm_100a fast path).
+//
+// Same algebra as bayer.cu (bayer.cuh); what changes is how bytes reach the SM:
+//   * a CUtensorMap describes the mosaic as a 3-D tensor (x in 32-bit words, y, frame);
+//   * a persistent grid of CTAs (a multiple of the SM count) walks the tile list;
+//     one elected thread issues `cp.async.bulk.tensor.3d` for tiles STAGES ahead,
+//     each landing a (TILE_W+32) x (TILE_H+2) byte box - the tile plus its 1-pixel
+//     stencil halo, 16 B of margin left/right so every lane reads aligned words -
+//     in a shared-memory ring, completion signalled on an mbarrier (no registers
+//     hold in-flight loads, so the prefetch depth does not cost occupancy);
+//   * 8 warps consume a tile: a warp marches down an 8-row strip of 128 pixels
+//     keeping the 3 upsampled rows of the stencil in registers, one 128-bit
+//     streaming store (4 RGBx pixels) per lane per row;
+//   * out-of-bounds box rows/columns arrive zero-filled; the frame-edge rules of the
+//     reference (top mirrors row 1, bottom reuses row h-4, left/right copies,
+//     gstbayer2rgb.c:360-380,429-448) are applied by row re-indexing inside the box
+//     and by the PRMT edge selectors, never by reading the zero fill.
+// Needs: source base/pitch/frame pitch multiples of 16 B (TMA), destination
+// 16-byte aligned. Everything else goes to bayer2rgb_direct.
+#include "bayer.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int TILE_W = 256;                 // output pixels per tile row
+constexpr int TILE_H = 32;
+constexpr int BOX_W = TILE_W + 32;          // bytes: 16 B margin each side (left halo byte at column 15)
+constexpr int BOX_H = TILE_H + 2;
+constexpr int STAGE_BYTES = ((BOX_W * BOX_H + 127) / 128) * 128;
+constexpr int STAGES = 4;
+constexpr int TMA_THREADS = 256;
+constexpr int STRIP = 8;                    // rows per warp per tile (TILE_H / 4 strips)
+
+struct TmaParams {
+  uint8_t *dst;
+  size_t dst_frame_stride;
+  int dst_stride;
+  int width, height, nframes;
+  int tiles_x, tiles_y;
+  int first_is_gr;
+};
+
+__device__ __forceinline__ uint32_t smem_u32 (const void *p) { return (uint32_t) __cvta_generic_to_shared (p); }
+
+__device__ __forceinline__ void mbar_init (uint64_t *bar, int count) {
+  asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx (uint64_t *bar, uint32_t bytes) {
+  asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32 (bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait (uint64_t *bar, uint32_t parity) {
+  asm volatile (
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" :: "r"(smem_u32 (bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d (void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile (
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :: "r"(smem_u32 (smem_dst)), "l"(map), "r"(smem_u32 (bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__device__ __forceinline__ void tile_coords (int t, const TmaParams &p, int &f, int &ty, int &tx) {
+  int per_frame = p.tiles_x * p.tiles_y;
+  f = t / per_frame;
+  int r = t - f * per_frame;
+  ty = r / p.tiles_x;
+  tx = r - ty * p.tiles_x;
+}
+
+template <int ORDER, int MODE>
+__global__ void __launch_bounds__ (TMA_THREADS)
+bayer2rgb_tma_kernel (const __grid_constant__ CUtensorMap src_map, const TmaParams p,
+    const __grid_constant__ BayerEpilogue epi)
+{
+  extern __shared__ __align__ (128) uint8_t smem_raw[];
+  // 128 B alignment of the dynamic window is guaranteed by the runtime for the first byte
+  uint8_t *stage_base = smem_raw;
+  uint32_t *epi_tab = reinterpret_cast<uint32_t *> (smem_raw + STAGES * STAGE_BYTES);
+  if (MODE != 0) lut_fill (epi_tab, epi.table);
+  const uint32_t *tl = epi_tab + (threadIdx.x & 31);
+  __shared__ __align__ (8) uint64_t full[STAGES];
+
+  const int ntiles = p.tiles_x * p.tiles_y * p.nframes;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init (&full[s], 1);
+    asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads ();
+
+  auto issue = [&] (int t, int s) {
+    int f, ty, tx;
+    tile_coords (t, p, f, ty, tx);
+    mbar_expect_tx (&full[s], BOX_W * BOX_H);
+    // x in 32-bit words: box starts 16 B left of the tile, one row above it
+    tma_load_3d (stage_base + s * STAGE_BYTES, &src_map, &full[s], tx * (TILE_W / 4) - 4, ty * TILE_H - 1, f);
+  };
+
+  if (tid == 0) {
+#pragma unroll 1
+    for (int s = 0; s < STAGES; s++) {
+      int t = blockIdx.x + s * gridDim.x;
+      if (t < ntiles) issue (t, s);
+    }
+  }
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int half = warp & 1, strip = warp >> 1;
+  const int xl = half * 128 + lane * 4;             // pixel x inside the tile
+  const int h = p.height, w = p.width;
+
+  int k = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, k++) {
+    const int s = k % STAGES;
+    const uint32_t parity = (k / STAGES) & 1;
+    int f, ty, tx;
+    tile_coords (t, p, f, ty, tx);
+    const int x0 = tx * TILE_W + xl;
+    const int y0 = ty * TILE_H;
+    const int j0 = y0 + strip * STRIP;
+    const int jend = min (j0 + STRIP, h);
+    const bool active = x0 < w;
+    const int v = min (4, w - x0);
+    const uint32_t selL = bayer_selL (x0);
+    const uint32_t selR = bayer_selR (active && x0 + 4 >= w, v);
+
+    mbar_wait (&full[s], parity);
+
+    if (j0 < jend) {
+      const uint8_t *box = stage_base + s * STAGE_BYTES + 16 + xl;       // column of this lane's word
+      // box row r holds global row y0 - 1 + r
+      auto load_row = [&] (int g) {
+        const uint8_t *rp = box + (g - (y0 - 1)) * BOX_W;
+        uint32_t prev = *reinterpret_cast<const uint32_t *> (rp - 4);
+        uint32_t cur = *reinterpret_cast<const uint32_t *> (rp);
+        uint32_t next = *reinterpret_cast<const uint32_t *> (rp + 4);
+        return bayer_upsample (prev, cur, next, selL, selR);
+      };
+      BayerRow u = load_row (j0 == 0 ? 1 : j0 - 1);
+      BayerRow c = load_row (j0);
+      uint8_t *o = p.dst + (size_t) f * p.dst_frame_stride + (size_t) j0 * p.dst_stride + (size_t) x0 * 4;
+#pragma unroll
+      for (int i = 0; i < STRIP; i++) {
+        const int jj = j0 + i;
+        if (jj < jend) {
+          int gd = (jj + 1 < h) ? jj + 1 : (h >= 4 ? h - 4 : 1);
+          BayerRow d = load_row (gd);
+          uint32_t R, G, B;
+          bayer_merge (u, c, d, ((jj & 1) != 0) != (p.first_is_gr != 0), R, G, B);
+          uint4 px = bayer_pack<ORDER> (R, G, B, 0xffffffffu);
+          px = bayer_epilogue<MODE> (px, tl, epi.luma_weights);
+          if (active) st_stream_v4 (o, px);                  // width % 4 == 0 on this path
+          o += p.dst_stride;
+          u = c;
+          c = d;
+        }
+      }
+    }
+    __syncthreads ();                      // every warp is done reading stage s
+    if (tid == 0) {
+      int tn = t + STAGES * gridDim.x;
+      if (tn < ntiles) issue (tn, s);
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn) (CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode (b200vf_ctx *ctx) {
+  if (!ctx->tma_encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint ("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    cudaGetLastError ();
+    ctx->tma_encode = fn;
+  }
+  return (EncodeTiledFn) ctx->tma_encode;
+}
+
+template <int ORDER, int MODE>
+int launch_tma_mode (b200vf_ctx *ctx, const CUtensorMap &map, const TmaParams &p, const BayerEpilogue &epi, cudaStream_t s) {
+  static bool attr_set = false;
+  const int smem = STAGES * STAGE_BYTES + (MODE ? LUT_SMEM_BYTES : 0);
+  if (!attr_set) {
+    B200VF_CHECK_CUDA (cudaFuncSetAttribute (bayer2rgb_tma_kernel<ORDER, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  int ntiles = p.tiles_x * p.tiles_y * p.nframes;
+  int grid = ctx->sm_count * (MODE ? 3 : 4);   // resident CTAs per SM: 39 KB (+32 KB table) of smem, 256 threads each
+  if (grid > ntiles) grid = ntiles;
+  bayer2rgb_tma_kernel<ORDER, MODE><<<grid, TMA_THREADS, smem, s>>> (map, p, epi);
+  return b200vf_launched (ctx, MODE ? "bayer2rgb_tma_fused" : "bayer2rgb_tma");
+}
+template <int ORDER>
+int launch_tma (b200vf_ctx *ctx, const CUtensorMap &map, const TmaParams &p, const BayerEpilogue &epi, cudaStream_t s) {
+  switch (epi.mode) {
+    case 0: return launch_tma_mode<ORDER, 0> (ctx, map, p, epi, s);
+    case 1: return launch_tma_mode<ORDER, 1> (ctx, map, p, epi, s);
+    default: return launch_tma_mode<ORDER, 2> (ctx, map, p, epi, s);
+  }
+}
+
+}  // namespace
+
+bool b200vf_bayer2rgb_tma_usable (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
+    const uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int height) {
+  if (((uintptr_t) d_src) % 16 || src_stride % 16 || src_frame_stride % 16) return false;
+  if (((uintptr_t) d_dst) % 16 || dst_stride % 16 || dst_frame_stride % 16) return false;
+  if (width % 4) return false;                 // the last word must be a full word (v == 4)
+  int rem = height % TILE_H;
+  if (rem == 1 || rem == 2) return false;      // row h-4 must lie inside the last tile's box
+  if (height < 4) return false;
+  return get_encode (ctx) != nullptr;
+}
+
+int b200vf_bayer2rgb_tma_launch (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
+    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int height, int nframes,
+    int order, int first_is_gr, const BayerEpilogue &epi, cudaStream_t s)
+{
+  EncodeTiledFn encode = get_encode (ctx);
+  B200VF_REQUIRE (encode, B200VF_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap map;
+  // 3-D tensor of 32-bit words: x (width/4 words; bytes past `width` inside the pitch are never used), y, frame
+  cuuint64_t gdim[3] = { (cuuint64_t) (width / 4), (cuuint64_t) height, (cuuint64_t) nframes };
+  cuuint64_t gstride[2] = { (cuuint64_t) src_stride, (cuuint64_t) (nframes > 1 ? src_frame_stride : (size_t) src_stride * height) };
+  cuuint32_t box[3] = { BOX_W / 4, BOX_H, 1 };
+  cuuint32_t estr[3] = { 1, 1, 1 };
+  CUresult r = encode (&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *) d_src, gdim, gstride, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200VF_REQUIRE (r == CUDA_SUCCESS, B200VF_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int) r);
+  TmaParams p;
+  p.dst = d_dst;
+  p.dst_frame_stride = dst_frame_stride;
+  p.dst_stride = dst_stride;
+  p.width = width;
+  p.height = height;
+  p.nframes = nframes;
+  p.tiles_x = (width + TILE_W - 1) / TILE_W;
+  p.tiles_y = (height + TILE_H - 1) / TILE_H;
+  p.first_is_gr = first_is_gr;
+  switch (order) {
+    case 0: return launch_tma<0> (ctx, map, p, epi, s);
+    case 1: return launch_tma<1> (ctx, map, p, epi, s);
+    case 2: return launch_tma<2> (ctx, map, p, epi, s);
+    default: return launch_tma<3> (ctx, map, p, epi, s);
+  }
+}

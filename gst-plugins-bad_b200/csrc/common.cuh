@@ -1,0 +1,94 @@
+// common.cuh - context, error plumbing and device helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include <string>
+#include "../../include/b200vf.h"
+
+#define B200VF_API extern "C" __attribute__((visibility("default")))
+
+struct b200vf_ctx {
+  int device = -1;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  std::atomic<uint64_t> launches{0};
+  const char *last_kernel = "";
+  int variant = 0;                 // 0 auto, 1 direct, 2 tma
+  void *tma_encode = nullptr;      // cuTensorMapEncodeTiled entry point (driver API via cudart)
+};
+
+void b200vf_set_error (const char *fmt, ...);
+
+#define B200VF_CHECK_CUDA(expr)                                                      \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      b200vf_set_error ("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,          \
+          cudaGetErrorString (_e));                                                  \
+      return B200VF_E_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
+
+#define B200VF_REQUIRE(cond, status, ...)                                            \
+  do {                                                                               \
+    if (!(cond)) {                                                                   \
+      b200vf_set_error (__VA_ARGS__);                                                \
+      return (status);                                                               \
+    }                                                                                \
+  } while (0)
+
+static inline cudaStream_t b200vf_stream (b200vf_ctx *ctx, void *stream) {
+  return stream ? (cudaStream_t) stream : ctx->stream;
+}
+
+// Every kernel launch goes through this so that gpu_launches is a count, not a guess.
+static inline int b200vf_launched (b200vf_ctx *ctx, const char *name) {
+  ctx->launches.fetch_add (1, std::memory_order_relaxed);
+  ctx->last_kernel = name;
+  cudaError_t e = cudaGetLastError ();
+  if (e != cudaSuccess) {
+    b200vf_set_error ("launch of %s failed: %s", name, cudaGetErrorString (e));
+    return B200VF_E_CUDA;
+  }
+  return B200VF_OK;
+}
+
+// Small constant tables (LUTs, gaussian taps, colour tables) travel as
+// __grid_constant__ kernel parameters: no staging buffer, nothing to
+// synchronise, and the op stays asynchronous and stream-ordered.
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- device side
+__device__ __forceinline__ uint32_t ldg_u32 (const void *p) {
+  return __ldg (reinterpret_cast<const unsigned int *> (p));
+}
+// streaming (read-once) 128-bit load / store: keep L1 for the data that is reused
+__device__ __forceinline__ uint4 ld_stream_v4 (const void *p) {
+  uint4 r;
+  asm volatile ("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_v4 (void *p, uint4 v) {
+  asm volatile ("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+      :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_v2 (void *p, uint2 v) {
+  asm volatile ("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};"
+      :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream_u32 (void *p, uint32_t v) {
+  asm volatile ("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+// per-byte rounded-up average of 4 packed u8 = ORC avgub = (a+b+1)>>1, in 4 ops
+__device__ __forceinline__ uint32_t avg4 (uint32_t a, uint32_t b) {
+  uint32_t t = ((a ^ b) & 0xfefefefeu) >> 1;
+  return (a | b) - t;
+}
+#define PRMT(a, b, sel) __byte_perm ((a), (b), (sel))
+#endif

@@ -1,0 +1,277 @@
+/* b200vf.h - C-ABI of the B200-native per-pixel video-filter hot path.
+ *
+ * This is the drop-in boundary: a GLib-free, torch-free
+ * `extern "C"` surface of plain pointers and sizes that the element shells
+ * of gst-plugins-bad's `bayer`, `gaudieffects`, `coloreffects` and
+ * `geometrictransform` plugins call from their transform vfuncs instead of
+ * their ORC / scalar C inner loops.  Each entry point names the reference
+ * interface it replaces (paths relative to the gst-plugins-bad 1.19.2 tree).
+ *
+ * Conventions
+ *   - every function returns B200VF_OK (0) or a negative b200vf_status; nothing
+ *     aborts; b200vf_last_error() gives a thread-local message;
+ *   - `d_` pointers are device (HBM) addresses on the context's GPU;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the context's own
+ *     stream); all work is asynchronous and stream-ordered, no call
+ *     synchronises unless it says so;
+ *   - `nframes`/`*_frame_stride`: every op takes a batch of equally shaped
+ *     frames laid out at a fixed byte pitch (how the HBM pool lays them out),
+ *     one launch for the whole batch; nframes = 1 for a single GstBuffer;
+ *   - there is NO CPU fallback: without an sm_100 device b200vf_ctx_create
+ *     fails with B200VF_E_NO_DEVICE and nothing else can be called.
+ */
+#ifndef B200VF_H
+#define B200VF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VF_VERSION_MAJOR 0
+#define B200VF_VERSION_MINOR 1
+
+typedef enum b200vf_status {
+  B200VF_OK = 0,
+  B200VF_E_INVAL = -1,        /* bad argument / outside the reference's domain */
+  B200VF_E_NO_DEVICE = -2,    /* no sm_100 GPU (the product has no CPU path)   */
+  B200VF_E_CUDA = -3,         /* a CUDA runtime/driver call failed             */
+  B200VF_E_NOMEM = -4,
+  B200VF_E_UNSUPPORTED = -5,  /* caps/format the reference element rejects too */
+  B200VF_E_NOT_NEGOTIATED = -6, /* GST_FLOW_NOT_NEGOTIATED analogue            */
+  B200VF_E_NCCL = -7,
+  B200VF_E_PROPERTY = -8      /* unknown property / out-of-range value         */
+} b200vf_status;
+
+typedef struct b200vf_ctx b200vf_ctx;
+typedef struct b200vf_pool b200vf_pool;
+typedef struct b200vf_element b200vf_element;
+typedef struct b200vf_comm b200vf_comm;
+
+/* ------------------------------------------------------------------ context */
+int b200vf_version (void);                       /* major*100 + minor */
+const char *b200vf_last_error (void);
+const char *b200vf_status_string (int status);
+
+/* Binds to CUDA device `device` (must be compute capability 10.x), creates the
+ * context's stream. Mirrors the "register nothing if the driver is missing"
+ * rule of sys/nvcodec/plugin.c:72-103. */
+int b200vf_ctx_create (int device, b200vf_ctx **out);
+void b200vf_ctx_destroy (b200vf_ctx *ctx);
+int b200vf_ctx_device (const b200vf_ctx *ctx);
+void *b200vf_ctx_stream (const b200vf_ctx *ctx);
+int b200vf_ctx_sm_count (const b200vf_ctx *ctx);
+int b200vf_ctx_synchronize (b200vf_ctx *ctx, void *stream);
+/* Number of kernels this library has launched on this context so far (the
+ * bench's `gpu_launches` claim is the difference across the timed region). */
+uint64_t b200vf_ctx_launch_count (const b200vf_ctx *ctx);
+/* Name of the kernel variant the last call on this context dispatched to
+ * (e.g. "bayer2rgb_tma", "bayer2rgb_direct"); for tests and profiles. */
+const char *b200vf_ctx_last_kernel (const b200vf_ctx *ctx);
+/* Force a kernel variant for A/B measurements: 0 auto, 1 direct (no TMA), 2 TMA. */
+int b200vf_ctx_set_variant (b200vf_ctx *ctx, int variant);
+
+/* ---------------------------------------------------------- HBM buffer pool
+ * Replaces the default system-memory GstVideoBufferPool the elements get today
+ * (none of them overrides propose/decide_allocation); modelled on
+ * sys/nvcodec/gstcudabufferpool.c:55-222 + gstcudamemory.c:95-407: device
+ * storage is primary, a pinned host staging buffer is created lazily.
+ * Buffers have `buf_bytes` usable bytes + >= 64 zeroed slack bytes (D5). */
+int b200vf_pool_create (b200vf_ctx *ctx, size_t buf_bytes, int n_bufs, b200vf_pool **out);
+void b200vf_pool_destroy (b200vf_pool *pool);
+int b200vf_pool_acquire (b200vf_pool *pool, int *buf_index);      /* B200VF_E_NOMEM when drained */
+int b200vf_pool_release (b200vf_pool *pool, int buf_index);
+void *b200vf_pool_device_ptr (b200vf_pool *pool, int buf_index);
+void *b200vf_pool_host_ptr (b200vf_pool *pool, int buf_index);   /* pinned staging, lazily allocated */
+size_t b200vf_pool_buf_bytes (const b200vf_pool *pool);
+size_t b200vf_pool_buf_pitch (const b200vf_pool *pool);           /* bytes between consecutive buffers */
+int b200vf_pool_upload (b200vf_pool *pool, int buf_index, const void *host_src, size_t bytes, void *stream);
+int b200vf_pool_download (b200vf_pool *pool, int buf_index, void *host_dst, size_t bytes, void *stream);
+/* Raw helpers for callers that own their memory. */
+int b200vf_malloc (b200vf_ctx *ctx, size_t bytes, void **d_out);  /* zero-filled, +64 B slack */
+int b200vf_free (b200vf_ctx *ctx, void *d_ptr);
+int b200vf_host_alloc (size_t bytes, void **h_out);               /* pinned */
+int b200vf_host_free (void *h_ptr);
+int b200vf_memcpy_h2d (b200vf_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream);
+int b200vf_memcpy_d2h (b200vf_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream);
+
+/* -------------------------------------------------------------- bayer plugin
+ * b200vf_bayer2rgb replaces gst_bayer2rgb_process (gst/bayer/gstbayer2rgb.c:
+ * 387-451) and the ORC programs it drives (gstbayerorc.orc:3-248).
+ *   pattern: 0 bggr, 1 gbrg, 2 grbg, 3 rggb   (enum gstbayer2rgb.c:95-101)
+ *   r_off/g_off/b_off: GST_VIDEO_INFO_COMP_OFFSET of the negotiated src format
+ *     (gstbayer2rgb.c:269-271); must be one of the four triples the reference
+ *     dispatches on (:409-421): (2,1,0) (3,2,1) (1,2,3) (0,1,2); the remaining
+ *     byte is written 255.
+ *   src_stride is GST_ROUND_UP_4(width) in the element (:477); dst_stride 4*width.
+ *   Domain: even width >= 4, height >= 3 (else B200VF_E_INVAL; the reference
+ *   reads uninitialised memory there). Edge rules reproduced bit-exactly: top
+ *   mirrors row 1, bottom uses row height-4, right edge copies (:372-380). */
+int b200vf_bayer2rgb (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
+    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int height, int nframes,
+    int pattern, int r_off, int g_off, int b_off, void *stream);
+
+/* Row-sharded variant (multi-GPU): this rank owns global rows
+ * [row0, row0+rows) of a frame of `full_height` rows; d_src points at the
+ * shard's first row and must be preceded by one valid halo row and followed by
+ * one (the rows b200vf_comm_halo_exchange fills); the global edge rules are
+ * applied with global row indices, the bottom rule (row height-4) reads
+ * d_bottom_m4 = pointer to global row full_height-4 if this rank owns the
+ * last row (it lies inside the last shard when that shard has >= 4 rows). */
+int b200vf_bayer2rgb_shard (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
+    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int full_height, int row0, int rows,
+    int nframes, int pattern, int r_off, int g_off, int b_off, void *stream);
+
+/* Replaces the per-pixel select loop of gst_rgb2bayer_transform
+ * (gst/bayer/gstrgb2bayer.c:254-267); src is ARGB (4 B/px). */
+int b200vf_rgb2bayer (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
+    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int height, int nframes,
+    int pattern, void *stream);
+
+/* ------------------------------------------------------- gaudieffects plugin
+ * Per-byte-position LUT over packed 4-byte pixels: out.byte[c] = lut[c][in.byte[c]].
+ * Replaces gaudi_orc_burn (gstgaudieffectsorc.orc:1-25) and the static
+ * transform() loops of gstdodge.c:231-254, gstchromium.c:282-338,
+ * gstsolarize.c:286-339 (all pure per-channel functions) and the per-channel
+ * presets of coloreffects. LUT builders below reproduce each element's
+ * arithmetic on the host (libm cos for chromium stays on the host, §8c-ii).
+ * npix = width*height (the reference loops flat, stride == 4*width). */
+int b200vf_lut4 (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, size_t npix_total,
+    const uint8_t lut[4][256], void *stream);
+int b200vf_lut_burn (int adjustment, uint8_t lut[4][256]);                 /* gstburn.c:214-250 */
+int b200vf_lut_dodge (uint8_t lut[4][256]);                                /* gstdodge.c:231-254 */
+int b200vf_lut_chromium (int edge_a, int edge_b, uint8_t lut[4][256]);     /* gstchromium.c:282-338 */
+int b200vf_lut_solarize (int threshold, int start, int end, uint8_t lut[4][256]); /* gstsolarize.c:286-339 */
+/* lut_out[c][v] = second[c][first[c][v]] : host-side fusion of consecutive per-channel elements */
+int b200vf_lut_compose (const uint8_t first[4][256], const uint8_t second[4][256], uint8_t lut_out[4][256]);
+
+/* gstexclusion.c:256-284 (red uses green*red, :269-270); factor in [1,175]. */
+int b200vf_exclusion (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, size_t npix_total,
+    int factor, void *stream);
+
+/* gstdilate.c:258-345; frames of width x height u32 pixels, stride 4*width.
+ * d_below (may be NULL) = the row under the last row when the frame is a row
+ * shard (else the last row's `down` neighbour is itself). */
+int b200vf_dilate (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, int width, int height,
+    size_t frame_stride, int nframes, int erode, const uint8_t *d_below, void *stream);
+
+/* gaussianblur. b200vf_gauss_kernel = make_gaussian_kernel (gstgaussblur.c:
+ * 361-422) on the host (libm pow/sqrt); returns windowsize (odd, <= 101) or <0.
+ * b200vf_gaussblur = gaussian_smooth + blur_row_x (:259-356) with the element's
+ * gst_video_frame_copy (:252) folded in: d_dst receives the whole frame, bytes
+ * [p0, p0 + 4*width*height) blurred (p0 = COMP_OFFSET of component 0: 1 for
+ * AYUV), other bytes copied. exact != 0: separate fp32 multiply and
+ * add in the reference's tap order (bit-exact); exact == 0: fused multiply-add
+ * (faster, within 1 LSB of the u8 output). Row-shard arguments: the frame is
+ * rows [row0,row0+rows) of full_height; halo rows (center above/below) must be
+ * present around d_src unless at the global edge. */
+int b200vf_gauss_kernel (float sigma, float *kernel, float *kernel_sum, int capacity);
+int b200vf_gaussblur (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, int width, int full_height,
+    int row0, int rows, int stride, size_t frame_stride, int nframes, int p0,
+    const float *kernel, const float *kernel_sum, int windowsize, int exact, void *stream);
+
+/* ------------------------------------------------------- coloreffects plugin
+ * In place (transform_frame_ip, gstcoloreffects.c:479-501).
+ * table: one of the five 256x3 preset tables (b200vf_coloreffects_table);
+ * map_luma as set per preset (:503-548); offs = COMP_POFFSET of R,G,B (or
+ * Y,U,V); pixel_stride 3 or 4; row_stride in bytes.
+ * b200vf_coloreffects_rgb replaces gst_color_effects_transform_rgb (:303-359),
+ * b200vf_coloreffects_ayuv replaces gst_color_effects_transform_ayuv (:361-435). */
+int b200vf_coloreffects_table (int preset, const uint8_t **table768, int *map_luma); /* 1 heat..5 yellowblue */
+int b200vf_coloreffects_rgb (b200vf_ctx *ctx, uint8_t *d_data, int width, int height, int row_stride,
+    size_t frame_stride, int nframes, int pixel_stride, int off_r, int off_g, int off_b,
+    const uint8_t *table768, int map_luma, void *stream);
+int b200vf_coloreffects_ayuv (b200vf_ctx *ctx, uint8_t *d_data, int width, int height, int row_stride,
+    size_t frame_stride, int nframes, int off_y, int off_u, int off_v,
+    const uint8_t *table768, int map_luma, void *stream);
+/* gst_chroma_hold_process_xrgb (gstchromahold.c:317-360), in place, 4 B/px. */
+int b200vf_chromahold (b200vf_ctx *ctx, uint8_t *d_data, int width, int height, int row_stride,
+    size_t frame_stride, int nframes, int off_r, int off_g, int off_b,
+    int target_r, int target_g, int target_b, int tolerance, void *stream);
+
+/* -------------------------------------------------- geometrictransform plugin
+ * The reference precomputes a gdouble (x,y) map per output pixel with libm on
+ * the CPU (gst_geometric_transform_generate_map, gstgeometrictransform.c:80-128)
+ * and resolves it per frame in do_map (:167-207). Here the host resolves the
+ * map ONCE into a compact int32 source-pixel index per output pixel
+ * (ty*width+tx, or -1 = keep the fill value) with exactly do_map's off-edge
+ * policy and truncation, and the kernel gathers.
+ *   element: "fisheye" "circle" ... (the 16 factory names of plugin.c:40-62,
+ *   `diffuse` excluded: per-frame RNG). props: element properties as name/value
+ *   pairs ("x-center", "zoom", ...; enum/int properties as doubles).
+ *   off_edge: 0 ignore, 1 clamp, 2 wrap (enum :57-75). */
+int b200vf_gt_build_map (const char *element, int width, int height, const char *const *prop_names,
+    const double *prop_values, int nprops, double *map_xy /* [height][width][2] */);
+int b200vf_gt_resolve_map (const double *map_xy, int width, int height, int off_edge, int32_t *index_out);
+/* fill: 32-bit pattern the cleared frame holds (0, or 0x808010ff for AYUV =
+ * GST_WRITE_UINT32_BE(0xff108080), :244-252); pixel_stride 1,2,3 or 4. */
+int b200vf_remap (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, const int32_t *d_index,
+    int width, int height, int pixel_stride, int row_stride, size_t frame_stride, int nframes,
+    uint32_t fill, void *stream);
+
+/* ------------------------------------------------------------ fused chains
+ * bayer2rgb followed by per-channel LUT elements (coloreffects per-channel
+ * presets, burn, dodge, chromium, solarize, composed on the host) and/or one
+ * luma-mapped coloreffects preset, in ONE kernel: 5 B/px instead of 5+8+8
+ * (BASELINE.json config 5). lut (may be NULL) is applied per output byte
+ * position; luma_table768 (may be NULL) is a map_luma preset applied first. */
+int b200vf_bayer2rgb_fused (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
+    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int height, int nframes,
+    int pattern, int r_off, int g_off, int b_off, const uint8_t *luma_table768,
+    const uint8_t lut[4][256], void *stream);
+
+/* ------------------------------------------------------ multi-GPU row shards
+ * One process per GPU. The communicator wraps NCCL (dlopen'd libnccl.so.2, so
+ * single-GPU users need no NCCL): the caller distributes the 128-byte unique
+ * id from rank 0 by whatever means it has. */
+int b200vf_comm_unique_id (uint8_t id_out[128]);
+int b200vf_comm_create (b200vf_ctx *ctx, const uint8_t id[128], int rank, int nranks, b200vf_comm **out);
+void b200vf_comm_destroy (b200vf_comm *comm);
+/* Even split of `height` rows into nranks blocks with even row0. */
+int b200vf_shard_rows (int height, int rank, int nranks, int *row0, int *rows);
+/* Halo exchange for a row-sharded buffer of nframes frames: each rank's shard
+ * of `rows` rows (row_bytes each) sits at d_shard + halo*row_bytes inside a
+ * buffer with `halo` rows of head-room above and below per frame
+ * (frame_stride bytes between frames); sends its first/last `halo` rows to the
+ * upper/lower neighbour and receives theirs into the head-room, one grouped
+ * ncclSend/ncclRecv per neighbour on `stream`. */
+int b200vf_comm_halo_exchange (b200vf_comm *comm, uint8_t *d_buf, size_t row_bytes, int rows, int halo,
+    size_t frame_stride, int nframes, void *stream);
+int b200vf_comm_barrier (b200vf_comm *comm, void *stream);
+
+/* ----------------------------------------------------- element mirror (host)
+ * A GLib-free mirror of the reference's element surface so pipelines can be
+ * driven, and parity tests written, the way the reference's would be:
+ * factory name -> element, GObject-style properties by name with the
+ * reference's ranges/defaults, caps-style negotiation, and the
+ * transform vfunc on HOST buffers (upload -> kernel -> download through the
+ * HBM pool, the path a sysmem pipeline takes) or on device buffers.
+ * Factory names: bayer2rgb rgb2bayer burn chromium dilate dodge exclusion
+ * gaussianblur solarize coloreffects chromahold + the geometrictransform set. */
+int b200vf_element_factory_make (b200vf_ctx *ctx, const char *factory, b200vf_element **out);
+void b200vf_element_destroy (b200vf_element *e);
+const char *b200vf_element_factory_name (const b200vf_element *e);
+/* Properties as doubles (uint/int/bool/enum/double all fit); enum properties
+ * also by nick through set_property_string ("preset"="sepia", "off-edge-pixels"="clamp"). */
+int b200vf_element_set_property (b200vf_element *e, const char *name, double value);
+int b200vf_element_set_property_string (b200vf_element *e, const char *name, const char *value);
+int b200vf_element_get_property (const b200vf_element *e, const char *name, double *value);
+/* Negotiation: format strings as in caps ("bggr", "RGBA", "AYUV", ...).
+ * Returns B200VF_E_UNSUPPORTED for formats outside the element's pad template. */
+int b200vf_element_set_caps (b200vf_element *e, const char *in_format, const char *out_format,
+    int width, int height);
+/* Frame sizes implied by the negotiated caps (get_unit_size, gstbayer2rgb.c:324-352). */
+int b200vf_element_unit_size (const b200vf_element *e, size_t *in_bytes, size_t *out_bytes);
+/* transform / transform_frame / transform_frame_ip on host memory: nframes
+ * frames packed back to back; pipelined H2D / kernel / D2H; synchronous. */
+int b200vf_element_transform_host (b200vf_element *e, const void *h_in, void *h_out, int nframes);
+/* The same vfunc on device memory, asynchronous on `stream`. For in-place
+ * elements d_out may equal d_in. */
+int b200vf_element_transform_device (b200vf_element *e, const void *d_in, void *d_out, int nframes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VF_H */

@@ -332,6 +332,36 @@ def gt_element(name, cfile, struct_body, cast, mapf, prepare=None, is_circle=Fal
 
 
 gt_element("fisheye", "gstfisheye.c", "GstGeometricTransform element;", "GST_FISHEYE_CAST", "fisheye_map")
+C = "GstCircleGeometricTransform element;"
+Gt = "GstGeometricTransform element;"
+gt_element("bulge", "gstbulge.c", C + " gdouble zoom;", "GST_BULGE_CAST", "bulge_map", is_circle=True,
+           props=[("zoom", "zoom", "gdouble")])
+gt_element("circle", "gstcircle.c", C + " gdouble angle; gdouble spread_angle; gint height;", "GST_CIRCLE_CAST", "circle_map",
+           is_circle=True, props=[("angle", "angle", "gdouble"), ("spread_angle", "spread_angle", "gdouble"), ("height", "height", "gint")])
+gt_element("kaleidoscope", "gstkaleidoscope.c", C + " gdouble angle; gdouble angle2; gint sides;", "GST_KALEIDOSCOPE_CAST",
+           "kaleidoscope_map", is_circle=True,
+           props=[("angle", "angle", "gdouble"), ("angle2", "angle2", "gdouble"), ("sides", "sides", "gint")])
+gt_element("pinch", "gstpinch.c", C + " gdouble intensity;", "GST_PINCH_CAST", "pinch_map", is_circle=True,
+           props=[("intensity", "intensity", "gdouble")])
+gt_element("rotate", "gstrotate.c", Gt + " gdouble angle;", "GST_ROTATE_CAST", "rotate_map", props=[("angle", "angle", "gdouble")])
+gt_element("sphere", "gstsphere.c", C + " gdouble refraction;", "GST_SPHERE_CAST", "sphere_map", is_circle=True,
+           props=[("refraction", "refraction", "gdouble")])
+gt_element("twirl", "gsttwirl.c", C + " gdouble angle;", "GST_TWIRL_CAST", "twirl_map", is_circle=True,
+           props=[("angle", "angle", "gdouble")])
+gt_element("waterripple", "gstwaterripple.c", C + " gdouble phase; gdouble amplitude; gdouble wavelength;", "GST_WATER_RIPPLE_CAST",
+           "water_ripple_map", is_circle=True,
+           props=[("phase", "phase", "gdouble"), ("amplitude", "amplitude", "gdouble"), ("wavelength", "wavelength", "gdouble")])
+gt_element("stretch", "gststretch.c", C + " gdouble intensity;", "GST_STRETCH_CAST", "stretch_map", is_circle=True,
+           extra_pre="#define MAX_SHRINK_AMOUNT 3.0\n", props=[("intensity", "intensity", "gdouble")])
+gt_element("tunnel", "gsttunnel.c", C, "GST_TUNNEL_CAST", "tunnel_map", is_circle=True)
+gt_element("square", "gstsquare.c", Gt + " gdouble width, height; gdouble zoom;", "GST_SQUARE_CAST", "square_map",
+           props=[("width", "width", "gdouble"), ("height", "height", "gdouble"), ("zoom", "zoom", "gdouble")])
+gt_element("mirror", "gstmirror.c", Gt + " gint mode;", "GST_MIRROR_CAST", "mirror_map",
+           extra_pre="enum { GST_MIRROR_MODE_LEFT, GST_MIRROR_MODE_RIGHT, GST_MIRROR_MODE_TOP, GST_MIRROR_MODE_BOTTOM };\n"
+                     "#define g_assert_not_reached() do { } while (0)\n",
+           props=[("mode", "mode", "gint")])
+gt_element("perspective", "gstperspective.c", Gt + " gdouble matrix[9];", "GST_PERSPECTIVE_CAST", "perspective_map",
+           props=[("matrix_%d" % i, "matrix[%d]" % i, "gdouble") for i in range(9)])
 
 CIRCLE_PRECALC = None
 
@@ -342,6 +372,8 @@ def gt_tu(name):
     def gen():
         s = GT_SHIM
         s += "typedef struct { %s } RefElem_%s;\n" % (e["struct_body"], name)
+        tname = {"waterripple": "GstWaterRipple"}.get(name, "Gst" + name.capitalize())
+        s += "typedef RefElem_%s %s;\n" % (name, tname)
         s += "#define %s(o) ((RefElem_%s *)(o))\n" % (e["cast"], name)
         s += e["extra_pre"]
         for fn in e["extra_funcs"]:

@@ -179,7 +179,8 @@ class Port(_Base):
     def rgb_to_hue(self, r, g, b):
         return self.lib.oracle_rgb_to_hue(int(r), int(g), int(b))
 
-    def gt_map(self, element, width, height, **props):
+    def gt_map(self, element, width, height, props=None):
+        props = props or {}
         m = np.zeros((height, width, 2), np.float64)
         fn = getattr(self.lib, "oracle_map_" + element, None)
         if fn is None:
@@ -300,7 +301,8 @@ class Ref(_Base):
         return self.lib.ref_rgb_to_hue(int(r), int(g), int(b))
 
     # geometrictransform: element instance = calloc'd blob of the element's struct
-    def _gt_elem(self, element, width, height, pixel_stride=4, row_stride=None, off_edge="ignore", **props):
+    def _gt_elem(self, element, width, height, pixel_stride=4, row_stride=None, off_edge="ignore", props=None):
+        props = props or {}
         size_fn = getattr(self.lib, "ref_gt_%s_size" % element)
         size_fn.restype = C.c_size_t
         blob = C.create_string_buffer(size_fn())
@@ -316,8 +318,11 @@ class Ref(_Base):
         getattr(self.lib, "ref_gt_%s_prepare" % element)(blob)
         return blob, gt
 
-    def gt_map(self, element, width, height, **props):
-        blob, gt = self._gt_elem(element, width, height, **props)
+    def gt_map(self, element, width, height, props=None):
+        """props: the element's struct fields (x_center, zoom, ...). NOTE: the reference sets its
+        defaults in each element's init(); this harness starts from a zeroed struct, so callers
+        pass every field (tests/refprops.py holds the defaults)."""
+        blob, gt = self._gt_elem(element, width, height, props=props)
         mf = getattr(self.lib, "ref_gt_%s_map" % element)
         mf.restype = C.c_void_p
         m = np.zeros((height, width, 2), np.float64)

@@ -1,0 +1,92 @@
+"""bayer2rgb parity: CUDA path (through the C-ABI) vs the oracle, bit-exact.
+Matrix from SURVEY.md Appendix A: sizes x 4 patterns x 4 channel layouts x edge-exposing frames."""
+import numpy as np
+import pytest
+
+import frames
+from oracle import BAYER_FORMATS, RGB_OFFSETS
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(4, 3), (4, 4), (6, 5), (8, 8), (64, 33), (130, 20), (256, 17), (640, 480)]
+LAYOUTS = ["RGBA", "BGRA", "ARGB", "ABGR"]
+
+
+def run_gpu(ctx, src, w, h, fmt, out, nframes=1):
+    stride = src.shape[-1]
+    d_src = ctx.upload(src)
+    d_dst = ctx.alloc(nframes * h * w * 4)
+    ctx.bayer2rgb(d_src, stride, d_dst, 4 * w, w, h, BAYER_FORMATS[fmt], RGB_OFFSETS[out], nframes=nframes)
+    res = ctx.download(d_dst).reshape(nframes, h, 4 * w)
+    return res
+
+
+@pytest.mark.parametrize("variant", ["direct", "auto"])
+@pytest.mark.parametrize("w,h", SIZES)
+def test_random_all_patterns_layouts(ctx, orc, rng, w, h, variant):
+    ctx.set_variant(variant)
+    try:
+        src = frames.random_u8(rng, h, frames.round_up_4(w))
+        for fmt in BAYER_FORMATS:
+            for out in LAYOUTS:
+                want = orc.bayer2rgb(src, w, h, fmt, out)
+                got = run_gpu(ctx, src, w, h, fmt, out)[0]
+                assert np.array_equal(got, want), (w, h, fmt, out, ctx.last_kernel(), np.argwhere(got != want)[:4])
+    finally:
+        ctx.set_variant("auto")
+
+
+@pytest.mark.parametrize("w,h", [(8, 8), (130, 20), (512, 64)])
+def test_edge_exposing_frames(ctx, orc, w, h):
+    stride = frames.round_up_4(w)
+    cases = [np.full((h, stride), 77, np.uint8), frames.checker_u8(h, stride)]
+    for (y, x) in [(0, 0), (1, 1), (0, w - 1), (1, w - 2), (h - 1, 0), (h - 1, w - 1), (h - 2, w - 3), (h - 4, 3), (h // 2, w // 2)]:
+        cases.append(frames.hot_pixel_u8(h, stride, y, x))
+    for src in cases:
+        for fmt in BAYER_FORMATS:
+            want = orc.bayer2rgb(src, w, h, fmt, "RGBA")
+            got = run_gpu(ctx, src, w, h, fmt, "RGBA")[0]
+            assert np.array_equal(got, want), (w, h, fmt)
+
+
+def test_batch_of_frames(ctx, orc, rng):
+    w, h, n = 256, 48, 5
+    src = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    got = run_gpu(ctx, src, w, h, "bggr", "BGRA", nframes=n)
+    for i in range(n):
+        assert np.array_equal(got[i], orc.bayer2rgb(src[i], w, h, "bggr", "BGRA")), i
+
+
+def test_videotestsrc_like_640x480_bggr_bgrx(ctx, orc):
+    """BASELINE.json configs[0]: bayer2rgb bggr -> BGRx 640x480."""
+    w, h = 640, 480
+    src = frames.mosaic_from_rgbx(frames.bars_rgbx(w, h), w, h, "bggr")
+    got = run_gpu(ctx, src, w, h, "bggr", "BGRx")[0]
+    assert np.array_equal(got, orc.bayer2rgb(src, w, h, "bggr", "BGRx"))
+
+
+def test_domain_errors(ctx, vf):
+    d = ctx.alloc(4096)
+    for (w, h) in [(5, 8), (2, 8), (8, 2)]:
+        with pytest.raises(vf.B200vfError) as e:
+            ctx.bayer2rgb(d, 8, d, 4 * w, w, h, 0, (0, 1, 2))
+        assert e.value.status == vf.E_INVAL
+    with pytest.raises(vf.B200vfError) as e:
+        ctx.bayer2rgb(d, 8, d, 32, 8, 8, 0, (0, 2, 1))      # not one of the four dispatched layouts
+    assert e.value.status == vf.E_UNSUPPORTED
+
+
+def test_4k_full_size_properties(ctx, orc, rng):
+    """BASELINE.json configs[1] size: bit-exact on a band sample + size-independent properties."""
+    w, h = 3840, 2160
+    src = frames.random_u8(rng, h, w)
+    got = run_gpu(ctx, src, w, h, "bggr", "RGBA")[0].reshape(h, w, 4)
+    # alpha is 255 everywhere; the real samples pass through untouched (B at even/even, R at odd/odd, G elsewhere)
+    assert (got[:, :, 3] == 255).all()
+    assert np.array_equal(got[0::2, 0::2, 2], src[0::2, 0::2])
+    assert np.array_equal(got[1::2, 1::2, 0], src[1::2, 1::2])
+    assert np.array_equal(got[0::2, 1::2, 1], src[0::2, 1::2])
+    assert np.array_equal(got[1::2, 0::2, 1], src[1::2, 0::2])
+    # full-frame bit-exact vs the oracle (the C oracle takes ~20 ms at 4K)
+    want = orc.bayer2rgb(src, w, h, "bggr", "RGBA").reshape(h, w, 4)
+    assert np.array_equal(got, want)

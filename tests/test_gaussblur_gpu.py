@@ -1,0 +1,89 @@
+"""gaussianblur parity through the C-ABI. exact=1 is bit-exact (separate fp32 mul/add in the
+reference's tap order); exact=0 (FMA) must stay within 1 LSB of the u8 output."""
+import numpy as np
+import pytest
+
+import frames
+
+pytestmark = pytest.mark.gpu
+
+
+def run(ctx, vf, frame, w, h, sigma, p0, exact=True):
+    k, ks = vf.gauss_kernel(sigma)
+    stride = frame.shape[1]
+    d_src = ctx.upload(frame)
+    d_dst = ctx.alloc(frame.size)
+    ctx.gaussblur(d_src, d_dst, w, h, stride, p0, k, ks, exact=exact)
+    return ctx.download(d_dst, frame.size).reshape(frame.shape)
+
+
+@pytest.mark.parametrize("sigma", [-5, -1.2, 0, 0.3, 1.2, 5, 20])
+@pytest.mark.parametrize("p0", [0, 1, 2])
+def test_sigmas_small_frames(ctx, vf, orc, rng, sigma, p0):
+    for (w, h) in [(8, 8), (40, 30), (70, 66)]:      # 8x8 at sigma=5: both edges truncate at once; 70x66: > one tile
+        fr = frames.random_u8(rng, h, 4 * w)
+        got = run(ctx, vf, fr, w, h, sigma, p0)
+        want = orc.gaussblur(fr, w, h, sigma, p0)
+        assert np.array_equal(got, want), (sigma, p0, w, h, ctx.last_kernel(), np.abs(got.astype(int) - want).max(), np.argwhere(got != want)[:4])
+
+
+def test_kernel_taps_match_reference(vf, orc):
+    for sigma in [-20, -5, -1.2, 0, 0.3, 1.2, 2.0, 5, 12.5, 20]:
+        k, ks = vf.gauss_kernel(sigma)
+        rk, rks = orc.gauss_kernel(sigma)
+        assert np.array_equal(k.view(np.uint32), rk.view(np.uint32)), sigma
+        assert np.array_equal(ks.view(np.uint32), rks.view(np.uint32)), sigma
+
+
+def test_padded_stride(ctx, vf, orc, rng):
+    w, h = 50, 20
+    fr = frames.random_u8(rng, h, 4 * w + 8)
+    for p0 in (0, 1):
+        got = run(ctx, vf, fr, w, h, 1.2, p0)
+        assert np.array_equal(got, orc.gaussblur(fr, w, h, 1.2, p0)), p0
+
+
+def test_ayuv_default_sigma_640x480(ctx, vf, orc):
+    w, h = 640, 480
+    fr = frames.bars_rgbx(w, h)
+    got = run(ctx, vf, fr, w, h, 1.2, 1)
+    assert np.array_equal(got, orc.gaussblur(fr, w, h, 1.2, 1))
+
+
+def test_fma_mode_within_one_lsb(ctx, vf, orc, rng):
+    w, h = 128, 96
+    fr = frames.random_u8(rng, h, 4 * w)
+    got = run(ctx, vf, fr, w, h, 5, 1, exact=False)
+    want = orc.gaussblur(fr, w, h, 5, 1)
+    assert np.abs(got.astype(int) - want.astype(int)).max() <= 1      # tolerance: 1 LSB of the u8 output
+
+
+def test_row_sharded_equals_whole(ctx, vf, orc, rng):
+    """two row shards with 13(+1)-row halos reproduce the whole-frame result (global truncation rules)"""
+    w, h, sigma, p0 = 64, 80, 5, 1
+    fr = frames.random_u8(rng, h, 4 * w)
+    want = orc.gaussblur(fr, w, h, sigma, p0)
+    k, ks = vf.gauss_kernel(sigma)
+    d_src = ctx.upload(fr)
+    d_dst = ctx.alloc(fr.size)
+    stride = 4 * w
+    for (row0, rows) in [(0, 40), (40, 40)]:
+        ctx.gaussblur(d_src.ptr + row0 * stride, d_dst.ptr + row0 * stride, w, rows, stride, p0, k, ks,
+                      row0=row0, rows=rows, full_height=h)
+    got = ctx.download(d_dst, fr.size).reshape(fr.shape)
+    assert np.array_equal(got, want), np.argwhere(got != want)[:6]
+
+
+def test_4k_sigma5_band_exact(ctx, vf, orc, rng):
+    """BASELINE.json configs[2] geometry: 3840x2160, sigma=5. The CPU oracle needs ~1.7 s/frame at 4K,
+    so compare a 256-row band that contains the top edge exactly, plus a size-independent property
+    on the whole frame: a constant image stays constant."""
+    w, h = 3840, 2160
+    fr = frames.random_u8(rng, h, 4 * w)
+    got = run(ctx, vf, fr, w, h, 5, 1)
+    band = 256
+    want = orc.gaussblur(fr[: band + 13], w, band + 13, 5, 1)        # rows < band are unaffected by the cut at band+13
+    assert np.array_equal(got[:band], want[:band])
+    const = np.full((h, 4 * w), 93, np.uint8)
+    out = run(ctx, vf, const, w, h, 5, 0)                # p0 = 0: no channel reaches into the zero slack (D5)
+    assert (out == 93).all()
