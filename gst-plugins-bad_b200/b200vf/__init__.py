@@ -365,7 +365,7 @@ class Element:
 
     def __init__(self, ctx, factory):
         h = _vp()
-        check(lib.b200vf_element_factory_make(ctx.h, factory.encode(), C.byref(h)))
+        check(lib.b200vf_element_factory_make(ctx.h if ctx is not None else None, factory.encode(), C.byref(h)))
         self.h, self.ctx, self.factory = h, ctx, factory
 
     def close(self):

@@ -156,10 +156,10 @@ int bayer_direct_set_smem () {
 }  // namespace
 
 int b200vf_bayer2rgb_tma_launch (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
-    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int height, int nframes,
+    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int full_height, int row0, int rows, int nframes,
     int order, int first_is_gr, const BayerEpilogue &epi, cudaStream_t s);
 bool b200vf_bayer2rgb_tma_usable (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
-    const uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int height);
+    const uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int full_height, int row0, int rows);
 
 static int bayer_common (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
     uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int full_height, int row0, int rows,
@@ -193,12 +193,11 @@ static int bayer_common (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, 
     attr_set = true;
   }
 
-  bool whole = (row0 == 0 && rows == full_height);
-  if (allow_tma && whole && ctx->variant != 1 &&
+  if (allow_tma && ctx->variant != 1 &&
       b200vf_bayer2rgb_tma_usable (ctx, d_src, src_stride, src_frame_stride, d_dst, dst_stride, dst_frame_stride,
-          width, full_height))
+          width, full_height, row0, rows))
     return b200vf_bayer2rgb_tma_launch (ctx, d_src, src_stride, src_frame_stride, d_dst, dst_stride,
-        dst_frame_stride, width, full_height, nframes, order, first_is_gr, epi, s);
+        dst_frame_stride, width, full_height, row0, rows, nframes, order, first_is_gr, epi, s);
   B200VF_REQUIRE (ctx->variant != 2, B200VF_E_UNSUPPORTED,
       "bayer2rgb: the TMA variant was forced but this geometry needs the direct kernel");
 
@@ -249,7 +248,7 @@ B200VF_API int b200vf_bayer2rgb_shard (b200vf_ctx *ctx, const uint8_t *d_src, in
   if (row0 == 0 && rows < full_height)
     B200VF_REQUIRE (rows >= 2, B200VF_E_INVAL, "bayer2rgb_shard: the first shard needs >= 2 rows (has %d)", rows);
   return bayer_common (ctx, d_src, src_stride, src_frame_stride, d_dst, dst_stride, dst_frame_stride,
-      width, full_height, row0, rows, nframes, pattern, r_off, g_off, b_off, false, nullptr, nullptr, stream);
+      width, full_height, row0, rows, nframes, pattern, r_off, g_off, b_off, true, nullptr, nullptr, stream);
 }
 
 // ------------------------------------------------------------------ rgb2bayer

@@ -30,6 +30,17 @@ __device__ __forceinline__ BayerRow bayer_upsample (uint32_t prev, uint32_t s, u
   return r;
 }
 
+// interior words: no edge patching
+__device__ __forceinline__ BayerRow bayer_upsample_interior (uint32_t prev, uint32_t s, uint32_t next) {
+  uint32_t L = PRMT (prev, s, 0x6543);
+  uint32_t R = PRMT (s, next, 0x4321);
+  uint32_t A = avg4 (L, R);
+  BayerRow r;
+  r.h0 = PRMT (s, A, 0x7250);
+  r.h1 = PRMT (s, A, 0x3614);
+  return r;
+}
+
 __device__ __forceinline__ uint32_t bayer_selL (int x0) { return x0 == 0 ? 0x3214u : 0x3210u; }
 // v = number of valid pixels in this word (2 or 4); last = this word holds columns n-2,n-1
 __device__ __forceinline__ uint32_t bayer_selR (bool last, int v) {
@@ -50,6 +61,23 @@ __device__ __forceinline__ void bayer_merge (const BayerRow &u, const BayerRow &
     R = c.h1;
     B = va0;
     G = PRMT (c.h0, avg4 (va1, c.h0), 0x7250);  // even x: the real sample, odd x: averaged
+  }
+}
+
+// the same with the row's role known at compile time (unrolled strips)
+template <bool GR_ROW>
+__device__ __forceinline__ void bayer_merge_ct (const BayerRow &u, const BayerRow &c, const BayerRow &d,
+    uint32_t &R, uint32_t &G, uint32_t &B) {
+  const uint32_t va0 = avg4 (u.h0, d.h0);
+  const uint32_t va1 = avg4 (u.h1, d.h1);
+  if (!GR_ROW) {
+    B = c.h0;
+    R = va1;
+    G = PRMT (avg4 (va0, c.h1), c.h1, 0x7250);
+  } else {
+    R = c.h1;
+    B = va0;
+    G = PRMT (c.h0, avg4 (va1, c.h0), 0x7250);
   }
 }
 

@@ -32,10 +32,13 @@ constexpr int TMA_THREADS = 256;
 constexpr int STRIP = 8;                    // rows per warp per tile (TILE_H / 4 strips)
 
 struct TmaParams {
-  uint8_t *dst;
+  uint8_t *dst;               // first OUTPUT row of this call (global row `row0`), frame 0
   size_t dst_frame_stride;
   int dst_stride;
-  int width, height, nframes;
+  int width, full_height;     // frame geometry (edge rules use global rows)
+  int row0, rows;             // output rows [row0, row0+rows): the whole frame, or this rank's row shard
+  int buf_row0;               // global row held by tensor row 0 (row0-1 when a halo row precedes the shard)
+  int nframes;
   int tiles_x, tiles_y;
   int first_is_gr;
 };
@@ -73,13 +76,57 @@ __device__ __forceinline__ void tile_coords (int t, const TmaParams &p, int &f, 
   tx = r - ty * p.tiles_x;
 }
 
+// one Bayer row out of the staged box: this lane's word and its two neighbours (aligned LDS.32,
+// constant offsets from `rp`), upsampled. XEDGE = the tile touches the left/right frame edge.
+template <bool XEDGE>
+__device__ __forceinline__ BayerRow box_row (const uint8_t *rp, uint32_t selL, uint32_t selR) {
+  const uint32_t prev = *reinterpret_cast<const uint32_t *> (rp - 4);
+  const uint32_t cur = *reinterpret_cast<const uint32_t *> (rp);
+  const uint32_t next = *reinterpret_cast<const uint32_t *> (rp + 4);
+  if (XEDGE) return bayer_upsample (prev, cur, next, selL, selR);
+  return bayer_upsample_interior (prev, cur, next);
+}
+
+// Interior strip: all STRIP rows and their two stencil rows are plain rows of the box, so every
+// LDS has a compile-time offset, the bg/gr role of a row is a compile-time constant (FIG = role of
+// the strip's first row) and nothing is predicated (lanes right of the frame skip the strip).
+template <int ORDER, int MODE, bool XEDGE, int FIG>
+__device__ __forceinline__ void strip_fast (const uint8_t *rp /* box row of global row j0-1, this lane's column */,
+    uint8_t *o, int dst_stride, uint32_t selL, uint32_t selR, const uint32_t *tl, uint32_t wts)
+{
+  BayerRow u = box_row<XEDGE> (rp, selL, selR);
+  BayerRow c = box_row<XEDGE> (rp + BOX_W, selL, selR);
+#pragma unroll
+  for (int i = 0; i < STRIP; i += 2) {            // rows alternate roles: two rows per iteration, roles fixed
+    {
+      BayerRow d = box_row<XEDGE> (rp + (i + 2) * BOX_W, selL, selR);
+      uint32_t R, G, B;
+      bayer_merge_ct<FIG != 0> (u, c, d, R, G, B);
+      uint4 px = bayer_epilogue<MODE> (bayer_pack<ORDER> (R, G, B, 0xffffffffu), tl, wts);
+      st_stream_v4 (o, px);
+      o += dst_stride;
+      u = c;
+      c = d;
+    }
+    {
+      BayerRow d = box_row<XEDGE> (rp + (i + 3) * BOX_W, selL, selR);
+      uint32_t R, G, B;
+      bayer_merge_ct<FIG == 0> (u, c, d, R, G, B);
+      uint4 px = bayer_epilogue<MODE> (bayer_pack<ORDER> (R, G, B, 0xffffffffu), tl, wts);
+      st_stream_v4 (o, px);
+      o += dst_stride;
+      u = c;
+      c = d;
+    }
+  }
+}
+
 template <int ORDER, int MODE>
 __global__ void __launch_bounds__ (TMA_THREADS)
 bayer2rgb_tma_kernel (const __grid_constant__ CUtensorMap src_map, const TmaParams p,
     const __grid_constant__ BayerEpilogue epi)
 {
   extern __shared__ __align__ (128) uint8_t smem_raw[];
-  // 128 B alignment of the dynamic window is guaranteed by the runtime for the first byte
   uint8_t *stage_base = smem_raw;
   uint32_t *epi_tab = reinterpret_cast<uint32_t *> (smem_raw + STAGES * STAGE_BYTES);
   if (MODE != 0) lut_fill (epi_tab, epi.table);
@@ -98,8 +145,9 @@ bayer2rgb_tma_kernel (const __grid_constant__ CUtensorMap src_map, const TmaPara
     int f, ty, tx;
     tile_coords (t, p, f, ty, tx);
     mbar_expect_tx (&full[s], BOX_W * BOX_H);
-    // x in 32-bit words: box starts 16 B left of the tile, one row above it
-    tma_load_3d (stage_base + s * STAGE_BYTES, &src_map, &full[s], tx * (TILE_W / 4) - 4, ty * TILE_H - 1, f);
+    // x in 32-bit words: the box starts 16 B left of the tile and one row above it
+    tma_load_3d (stage_base + s * STAGE_BYTES, &src_map, &full[s], tx * (TILE_W / 4) - 4,
+        p.row0 + ty * TILE_H - 1 - p.buf_row0, f);
   };
 
   if (tid == 0) {
@@ -113,7 +161,8 @@ bayer2rgb_tma_kernel (const __grid_constant__ CUtensorMap src_map, const TmaPara
   const int warp = tid >> 5, lane = tid & 31;
   const int half = warp & 1, strip = warp >> 1;
   const int xl = half * 128 + lane * 4;             // pixel x inside the tile
-  const int h = p.height, w = p.width;
+  const int h = p.full_height, w = p.width;
+  const int row_end = p.row0 + p.rows;
 
   int k = 0;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x, k++) {
@@ -122,44 +171,49 @@ bayer2rgb_tma_kernel (const __grid_constant__ CUtensorMap src_map, const TmaPara
     int f, ty, tx;
     tile_coords (t, p, f, ty, tx);
     const int x0 = tx * TILE_W + xl;
-    const int y0 = ty * TILE_H;
+    const int y0 = p.row0 + ty * TILE_H;            // global row of the tile's first output row
     const int j0 = y0 + strip * STRIP;
-    const int jend = min (j0 + STRIP, h);
     const bool active = x0 < w;
-    const int v = min (4, w - x0);
+    const bool xedge = (tx == 0) || (tx == p.tiles_x - 1);
     const uint32_t selL = bayer_selL (x0);
-    const uint32_t selR = bayer_selR (active && x0 + 4 >= w, v);
+    const uint32_t selR = bayer_selR (active && x0 + 4 >= w, 4);
+    const uint8_t *box = stage_base + s * STAGE_BYTES + 16 + xl;     // box row r = global row y0 - 1 + r
+    uint8_t *o = p.dst + (size_t) f * p.dst_frame_stride + (size_t) (j0 - p.row0) * p.dst_stride + (size_t) x0 * 4;
+    const int fig = (p.first_is_gr ^ j0) & 1;       // role of the strip's first row: 0 = "bg", 1 = "gr"
 
     mbar_wait (&full[s], parity);
 
-    if (j0 < jend) {
-      const uint8_t *box = stage_base + s * STAGE_BYTES + 16 + xl;       // column of this lane's word
-      // box row r holds global row y0 - 1 + r
-      auto load_row = [&] (int g) {
-        const uint8_t *rp = box + (g - (y0 - 1)) * BOX_W;
-        uint32_t prev = *reinterpret_cast<const uint32_t *> (rp - 4);
-        uint32_t cur = *reinterpret_cast<const uint32_t *> (rp);
-        uint32_t next = *reinterpret_cast<const uint32_t *> (rp + 4);
-        return bayer_upsample (prev, cur, next, selL, selR);
-      };
+    // rows j0-1 .. j0+STRIP are ordinary frame rows (no top mirror, no bottom rule, nothing clipped)
+    const bool plain = (j0 >= 1) && (j0 + STRIP < h) && (j0 + STRIP <= row_end);
+    if (plain) {
+      const uint8_t *rp = box + (j0 - y0) * BOX_W;
+      if (!active) {
+      } else if (!xedge) {
+        if (fig) strip_fast<ORDER, MODE, false, 1> (rp, o, p.dst_stride, selL, selR, tl, epi.luma_weights);
+        else strip_fast<ORDER, MODE, false, 0> (rp, o, p.dst_stride, selL, selR, tl, epi.luma_weights);
+      } else {
+        if (fig) strip_fast<ORDER, MODE, true, 1> (rp, o, p.dst_stride, selL, selR, tl, epi.luma_weights);
+        else strip_fast<ORDER, MODE, true, 0> (rp, o, p.dst_stride, selL, selR, tl, epi.luma_weights);
+      }
+    } else if (j0 < row_end) {
+      // strips touching the top / bottom of the frame (or the end of the shard): rows re-indexed
+      // per the reference's edge rules (gstbayer2rgb.c:429-448), everything else identical
+      const int jend = min (j0 + STRIP, row_end);
+      auto load_row = [&] (int g) { return box_row<true> (box + (g - (y0 - 1)) * BOX_W, selL, selR); };
       BayerRow u = load_row (j0 == 0 ? 1 : j0 - 1);
       BayerRow c = load_row (j0);
-      uint8_t *o = p.dst + (size_t) f * p.dst_frame_stride + (size_t) j0 * p.dst_stride + (size_t) x0 * 4;
-#pragma unroll
-      for (int i = 0; i < STRIP; i++) {
-        const int jj = j0 + i;
-        if (jj < jend) {
-          int gd = (jj + 1 < h) ? jj + 1 : (h >= 4 ? h - 4 : 1);
-          BayerRow d = load_row (gd);
-          uint32_t R, G, B;
-          bayer_merge (u, c, d, ((jj & 1) != 0) != (p.first_is_gr != 0), R, G, B);
-          uint4 px = bayer_pack<ORDER> (R, G, B, 0xffffffffu);
-          px = bayer_epilogue<MODE> (px, tl, epi.luma_weights);
-          if (active) st_stream_v4 (o, px);                  // width % 4 == 0 on this path
-          o += p.dst_stride;
-          u = c;
-          c = d;
-        }
+#pragma unroll 1
+      for (int jj = j0; jj < jend; jj++) {
+        const int gd = (jj + 1 < h) ? jj + 1 : (h >= 4 ? h - 4 : 1);
+        BayerRow d = load_row (gd);
+        uint32_t R, G, B;
+        bayer_merge (u, c, d, ((jj ^ p.first_is_gr) & 1) != 0, R, G, B);
+        uint4 px = bayer_pack<ORDER> (R, G, B, 0xffffffffu);
+        px = bayer_epilogue<MODE> (px, tl, epi.luma_weights);
+        if (active) st_stream_v4 (o, px);
+        o += p.dst_stride;
+        u = c;
+        c = d;
       }
     }
     __syncthreads ();                      // every warp is done reading stage s
@@ -213,29 +267,38 @@ int launch_tma (b200vf_ctx *ctx, const CUtensorMap &map, const TmaParams &p, con
 }  // namespace
 
 bool b200vf_bayer2rgb_tma_usable (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
-    const uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int height) {
+    const uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int full_height, int row0, int rows) {
   if (((uintptr_t) d_src) % 16 || src_stride % 16 || src_frame_stride % 16) return false;
   if (((uintptr_t) d_dst) % 16 || dst_stride % 16 || dst_frame_stride % 16) return false;
-  if (width % 4) return false;                 // the last word must be a full word (v == 4)
-  int rem = height % TILE_H;
-  if (rem == 1 || rem == 2) return false;      // row h-4 must lie inside the last tile's box
-  if (height < 4) return false;
+  if (width % 4) return false;                 // the last word must be a full word
+  if (full_height < 4) return false;
+  if (row0 + rows == full_height) {            // row h-4 must lie inside the last tile's box
+    int rem = rows % TILE_H;
+    if (rem == 1 || rem == 2) return false;
+  }
+  if (row0 > 0 && ((uintptr_t) (d_src - src_stride)) % 16) return false;   // tensor base = the halo row above
   return get_encode (ctx) != nullptr;
 }
 
+// d_src points at global row `row0` (the shard's first row; one halo row above it when row0 > 0
+// and one below when the shard does not end the frame).
 int b200vf_bayer2rgb_tma_launch (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
-    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int height, int nframes,
+    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int full_height, int row0, int rows, int nframes,
     int order, int first_is_gr, const BayerEpilogue &epi, cudaStream_t s)
 {
   EncodeTiledFn encode = get_encode (ctx);
   B200VF_REQUIRE (encode, B200VF_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const int buf_row0 = row0 > 0 ? row0 - 1 : 0;
+  const int buf_end = (row0 + rows < full_height) ? row0 + rows + 1 : full_height;
+  const uint8_t *base = d_src - (size_t) (row0 - buf_row0) * src_stride;
   CUtensorMap map;
   // 3-D tensor of 32-bit words: x (width/4 words; bytes past `width` inside the pitch are never used), y, frame
-  cuuint64_t gdim[3] = { (cuuint64_t) (width / 4), (cuuint64_t) height, (cuuint64_t) nframes };
-  cuuint64_t gstride[2] = { (cuuint64_t) src_stride, (cuuint64_t) (nframes > 1 ? src_frame_stride : (size_t) src_stride * height) };
+  cuuint64_t gdim[3] = { (cuuint64_t) (width / 4), (cuuint64_t) (buf_end - buf_row0), (cuuint64_t) nframes };
+  cuuint64_t gstride[2] = { (cuuint64_t) src_stride,
+    (cuuint64_t) (nframes > 1 ? src_frame_stride : (size_t) src_stride * (buf_end - buf_row0)) };
   cuuint32_t box[3] = { BOX_W / 4, BOX_H, 1 };
   cuuint32_t estr[3] = { 1, 1, 1 };
-  CUresult r = encode (&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *) d_src, gdim, gstride, box, estr,
+  CUresult r = encode (&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *) base, gdim, gstride, box, estr,
       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200VF_REQUIRE (r == CUDA_SUCCESS, B200VF_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int) r);
@@ -244,10 +307,13 @@ int b200vf_bayer2rgb_tma_launch (b200vf_ctx *ctx, const uint8_t *d_src, int src_
   p.dst_frame_stride = dst_frame_stride;
   p.dst_stride = dst_stride;
   p.width = width;
-  p.height = height;
+  p.full_height = full_height;
+  p.row0 = row0;
+  p.rows = rows;
+  p.buf_row0 = buf_row0;
   p.nframes = nframes;
   p.tiles_x = (width + TILE_W - 1) / TILE_W;
-  p.tiles_y = (height + TILE_H - 1) / TILE_H;
+  p.tiles_y = (rows + TILE_H - 1) / TILE_H;
   p.first_is_gr = first_is_gr;
   switch (order) {
     case 0: return launch_tma<0> (ctx, map, p, epi, s);

@@ -86,9 +86,13 @@ __device__ __forceinline__ void st_stream_u32 (void *p, uint32_t v) {
   asm volatile ("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 // per-byte rounded-up average of 4 packed u8 = ORC avgub = (a+b+1)>>1, in 4 ops
+// ((a^b) & 0xfefefefe) is one LOP3 (truth table 0x28); written as PTX because the compiler
+// otherwise splits it into xor / shift / and-0x7f7f7f7f (one more ALU-pipe op per average, and this
+// byte math is ALU-pipe bound: PRMT/LOP3/SHF all issue there).
 __device__ __forceinline__ uint32_t avg4 (uint32_t a, uint32_t b) {
-  uint32_t t = ((a ^ b) & 0xfefefefeu) >> 1;
-  return (a | b) - t;
+  uint32_t t;
+  asm ("lop3.b32 %0, %1, %2, 0xfefefefe, 0x28;" : "=r"(t) : "r"(a), "r"(b));
+  return (a | b) - (t >> 1);
 }
 #define PRMT(a, b, sel) __byte_perm ((a), (b), (sel))
 #endif

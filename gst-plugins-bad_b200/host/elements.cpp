@@ -298,7 +298,9 @@ int run (b200vf_element *e, const uint8_t *d_in, uint8_t *d_out, int nframes, cu
 }  // namespace
 
 B200VF_API int b200vf_element_factory_make (b200vf_ctx *ctx, const char *factory, b200vf_element **out) {
-  B200VF_REQUIRE (ctx && factory && out, B200VF_E_INVAL, "element_factory_make: NULL argument");
+  // ctx may be NULL: properties and negotiation need no device (gst-inspect works without a GPU);
+  // the transform vfuncs then fail with B200VF_E_NO_DEVICE - there is no CPU path.
+  B200VF_REQUIRE (factory && out, B200VF_E_INVAL, "element_factory_make: NULL argument");
   for (const auto &f : factories ()) {
     if (strcmp (f.name, factory)) continue;
     b200vf_element *e = new b200vf_element ();
@@ -317,7 +319,7 @@ B200VF_API int b200vf_element_factory_make (b200vf_ctx *ctx, const char *factory
 
 B200VF_API void b200vf_element_destroy (b200vf_element *e) {
   if (!e) return;
-  cudaSetDevice (e->ctx->device);
+  if (e->ctx) cudaSetDevice (e->ctx->device);
   free_staging (e);
   for (int i = 0; i < kHostStreams; i++) if (e->hs[i]) cudaStreamDestroy (e->hs[i]);
   if (e->d_index) cudaFree (e->d_index);
@@ -336,6 +338,9 @@ B200VF_API int b200vf_element_set_property (b200vf_element *e, const char *name,
   if (p->type != P_DOUBLE)
     B200VF_REQUIRE (value == floor (value), B200VF_E_PROPERTY, "property `%s` of `%s` is integral, got %g", name, e->def->name, value);
   std::lock_guard<std::mutex> g (e->lock);
+  // Reference quirk kept for drop-in fidelity: marble installs "turbulence" under PROP_YSCALE
+  // (gstmarble.c:265-269), so the name reads and writes y-scale and the real turbulence stays 1.
+  if (!strcmp (e->def->name, "marble") && !strcmp (name, "turbulence")) name = "y-scale";
   if (e->props[name] != value) {
     e->props[name] = value;
     if (e->def->kind == K_GEOMETRIC) e->need_remap = true;     // gst_geometric_transform_set_need_remap
@@ -365,6 +370,7 @@ B200VF_API int b200vf_element_set_property_string (b200vf_element *e, const char
 
 B200VF_API int b200vf_element_get_property (const b200vf_element *e, const char *name, double *value) {
   B200VF_REQUIRE (e && name && value, B200VF_E_INVAL, "get_property: NULL argument");
+  if (!strcmp (e->def->name, "marble") && !strcmp (name, "turbulence")) name = "y-scale";   // see set_property
   auto it = e->props.find (name);
   B200VF_REQUIRE (it != e->props.end (), B200VF_E_PROPERTY, "element `%s` has no property `%s`", e->def->name, name);
   *value = it->second;
@@ -424,12 +430,14 @@ B200VF_API int b200vf_element_unit_size (const b200vf_element *e, size_t *in_byt
 B200VF_API int b200vf_element_transform_device (b200vf_element *e, const void *d_in, void *d_out, int nframes, void *stream) {
   B200VF_REQUIRE (e && d_in && d_out && nframes > 0, B200VF_E_INVAL, "transform: bad argument");
   B200VF_REQUIRE (e->negotiated, B200VF_E_NOT_NEGOTIATED, "%s: not negotiated yet", e->def->name);
+  B200VF_REQUIRE (e->ctx, B200VF_E_NO_DEVICE, "%s: element has no device context (there is no CPU path)", e->def->name);
   return run (e, (const uint8_t *) d_in, (uint8_t *) d_out, nframes, b200vf_stream (e->ctx, stream));
 }
 
 B200VF_API int b200vf_element_transform_host (b200vf_element *e, const void *h_in, void *h_out, int nframes) {
   B200VF_REQUIRE (e && h_in && h_out && nframes > 0, B200VF_E_INVAL, "transform: bad argument");
   B200VF_REQUIRE (e->negotiated, B200VF_E_NOT_NEGOTIATED, "%s: not negotiated yet", e->def->name);
+  B200VF_REQUIRE (e->ctx, B200VF_E_NO_DEVICE, "%s: element has no device context (there is no CPU path)", e->def->name);
   B200VF_CHECK_CUDA (cudaSetDevice (e->ctx->device));
   int rc = ensure_staging (e);
   if (rc) return rc;

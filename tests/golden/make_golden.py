@@ -1,0 +1,118 @@
+#!/usr/bin/env python3
+"""Generates the golden fixtures of tests/golden/ FROM THE REFERENCE ITSELF.
+
+Run where /root/reference is mounted (this container):   python tests/golden/make_golden.py
+  * golden_small.npz         - seeded inputs + outputs of the reference's own C (oracle/_ref, built by
+                               oracle/build_ref.py from /root/reference) for every op of the hot path;
+  * coloreffects_tables.npz  - the five 256x3 preset tables (data of gstcoloreffects.c:117-286);
+  * element_surface.json     - factory name -> properties (type/min/max/default) and pad-template formats,
+                               extracted from the reference's docs/plugins/gst_plugins_cache.json.
+The reference's tests hold no vectors for these elements, so these fixtures are what pins
+the oracle port when /root/reference is absent (the GPU box)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle          # noqa: E402
+import refprops        # noqa: E402
+
+REF = os.environ.get("B200VF_REFERENCE", "/root/reference")
+
+
+def main():
+    R = oracle.get("reference")
+    rng = np.random.default_rng(20260925)
+    g = {}
+    np.savez_compressed(os.path.join(HERE, "coloreffects_tables.npz"),
+                        **{p: R.coloreffects_table(p)[0] for p in ["heat", "sepia", "xray", "xpro", "yellowblue"]})
+    # bayer2rgb / rgb2bayer
+    for (w, h) in [(4, 3), (6, 5), (16, 10)]:
+        src = rng.integers(0, 256, (h, oracle.round_up_4(w)), dtype=np.uint8)
+        g["bayer_src_%dx%d" % (w, h)] = src
+        for f in oracle.BAYER_FORMATS:
+            for o in ["RGBA", "BGRA", "ARGB", "ABGR"]:
+                g["bayer_%dx%d_%s_%s" % (w, h, f, o)] = R.bayer2rgb(src, w, h, f, o)
+    argb = rng.integers(0, 256, (7, 4 * 9), dtype=np.uint8)
+    g["rgb2bayer_src"] = argb
+    for f in oracle.BAYER_FORMATS:
+        g["rgb2bayer_" + f] = R.rgb2bayer(argb, 9, 7, f)
+    # gaussianblur
+    fr = rng.integers(0, 256, (9, 4 * 12), dtype=np.uint8)
+    g["gauss_src"] = fr
+    for s in [-1.2, 0.3, 1.2, 5.0]:
+        k, ks = R.gauss_kernel(s)
+        g["gauss_kernel_%g" % s] = k
+        g["gauss_ksum_%g" % s] = ks
+        for p0 in (0, 1, 2):
+            g["gauss_%g_p%d" % (s, p0)] = R.gaussblur(fr, 12, 9, s, p0)
+    # point ops: every byte value in every channel + random pixels
+    b = np.arange(256, dtype=np.uint32)
+    px = np.concatenate([b | (b << 8) | (b << 16) | (b << 24), rng.integers(0, 2 ** 32, 256, dtype=np.uint32)])
+    g["px"] = px
+    for adj in [0, 1, 175, 256]:
+        g["burn_%d" % adj] = R.burn(px, adj)
+    g["dodge"] = R.dodge(px)
+    for a, bb in [(200, 1), (0, 0), (256, 256), (37, 255)]:
+        g["chromium_%d_%d" % (a, bb)] = R.chromium(px, a, bb)
+    for f in [1, 2, 100, 175]:
+        g["exclusion_%d" % f] = R.exclusion(px, f)
+    for t, s, e in [(127, 50, 185), (50, 50, 185), (100, 100, 100), (127, 185, 50), (10, 200, 30)]:
+        g["solarize_%d_%d_%d" % (t, s, e)] = R.solarize(px, t, s, e)
+    dsrc = rng.integers(0, 2 ** 32, (8, 16), dtype=np.uint32)
+    g["dilate_src"] = dsrc
+    g["dilate_0"] = R.dilate(dsrc, False)
+    g["dilate_1"] = R.dilate(dsrc, True)
+    # coloreffects / chromahold
+    for fmt in ["RGB", "BGRx", "ARGB", "AYUV"]:
+        ps = 3 if fmt == "RGB" else 4
+        w, h = 9, 5
+        cf = rng.integers(0, 256, (h, oracle.round_up_4(w * ps)), dtype=np.uint8)
+        g["ce_src_" + fmt] = cf
+        for pr in oracle.PRESETS:
+            g["ce_%s_%s" % (fmt, pr)] = R.coloreffects(cf, w, h, fmt, pr)
+    cf = rng.integers(0, 256, (6, 4 * 10), dtype=np.uint8)
+    g["ch_src"] = cf
+    for i, (tgt, tol) in enumerate([((255, 0, 0), 30), ((128, 128, 128), 0), ((0, 200, 30), 180)]):
+        g["ch_%d" % i] = R.chromahold(cf, 10, 6, "xRGB", tgt, tol)
+    # geometrictransform: maps (as raw doubles) and one gather per off-edge policy
+    w, h = 16, 12
+    gsrc = rng.integers(0, 256, (h, 4 * w), dtype=np.uint8)
+    g["gt_src"] = gsrc
+    for el, plist in refprops.CASES.items():
+        for i, props in enumerate(plist):
+            m = R.gt_map(el, w, h, refprops.full(el, props))
+            g["gt_map_%s_%d" % (el, i)] = m
+            if i == 0:
+                for oe in oracle.OFF_EDGE:
+                    g["gt_out_%s_%s" % (el, oe)] = R.remap(gsrc, m, w, h, 4, oe, False)
+    g["gt_out_fisheye_ayuv"] = R.remap(gsrc, g["gt_map_fisheye_0"] * 1.7 - 9.0, w, h, 4, "ignore", True)
+    np.savez_compressed(os.path.join(HERE, "golden_small.npz"), **g)
+
+    # element surface from the reference's own API dump
+    cache = json.load(open(os.path.join(REF, "docs", "plugins", "gst_plugins_cache.json")))
+    want = {"bayer": ["bayer2rgb", "rgb2bayer"], "gaudieffects": None, "coloreffects": None, "geometrictransform": None}
+    surf = {}
+    for plugin, only in want.items():
+        for name, el in cache[plugin]["elements"].items():
+            if only and name not in only:
+                continue
+            props = {}
+            for pn, pd in el.get("properties", {}).items():
+                if pn in ("name", "parent", "qos"):
+                    continue
+                props[pn] = {k: pd.get(k) for k in ("type", "min", "max", "default", "controllable") if k in pd}
+            pads = {pn: pd.get("caps") for pn, pd in el.get("pad-templates", {}).items()}
+            surf[name] = {"plugin": plugin, "klass": el.get("klass"), "hierarchy": el.get("hierarchy"), "properties": props,
+                          "pad-templates": pads}
+    json.dump(surf, open(os.path.join(HERE, "element_surface.json"), "w"), indent=1, sort_keys=True)
+    print("wrote %d arrays, %d elements" % (len(g), len(surf)))
+
+
+if __name__ == "__main__":
+    main()

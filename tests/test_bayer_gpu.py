@@ -90,3 +90,25 @@ def test_4k_full_size_properties(ctx, orc, rng):
     # full-frame bit-exact vs the oracle (the C oracle takes ~20 ms at 4K)
     want = orc.bayer2rgb(src, w, h, "bggr", "RGBA").reshape(h, w, 4)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("variant", ["direct", "auto"])
+@pytest.mark.parametrize("w,h,cuts", [(256, 96, [0, 32, 96]), (512, 200, [0, 66, 132, 200]), (64, 50, [0, 24, 50]),
+                                      (3840, 2160, [0, 270, 540, 2160])])
+def test_row_shards_equal_whole_frame(ctx, orc, rng, w, h, cuts, variant):
+    """b200vf_bayer2rgb_shard: each shard reads its halo rows from the neighbouring rows of the same buffer;
+    global edge rules (top mirror, bottom row h-4) apply with global row indices."""
+    ctx.set_variant(variant)
+    try:
+        src = frames.random_u8(rng, h, w)
+        want = orc.bayer2rgb(src, w, h, "grbg", "BGRA")
+        d_src = ctx.upload(src)
+        d_dst = ctx.alloc(h * w * 4)
+        kernels = set()
+        for r0, r1 in zip(cuts[:-1], cuts[1:]):
+            ctx.bayer2rgb_shard(d_src.ptr + r0 * w, w, d_dst.ptr + r0 * w * 4, 4 * w, w, h, r0, r1 - r0, 2, (2, 1, 0))
+            kernels.add(ctx.last_kernel())
+        got = ctx.download(d_dst).reshape(h, 4 * w)
+        assert np.array_equal(got, want), (kernels, np.argwhere(got != want)[:4])
+    finally:
+        ctx.set_variant("auto")

@@ -1,0 +1,235 @@
+"""CPU-only: the host side of the product (no kernels run): the C-ABI library loads and exports every
+symbol include/b200vf.h declares, fails loudly without a device, and its host-side builders (LUTs,
+gaussian taps, geometric maps, index resolution, shard partition, element surface) match the oracle."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+import refprops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = np.load(os.path.join(ROOT, "tests", "golden", "golden_small.npz"))
+
+
+def test_library_exports_every_declared_symbol(vf):
+    hdr = open(os.path.join(ROOT, "include", "b200vf.h")).read()
+    declared = set(re.findall(r"\b(b200vf_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"b200vf_status"}
+    assert declared, "no declarations parsed"
+    missing = [s for s in sorted(declared) if not hasattr(vf.lib, s)]
+    assert not missing, missing
+    assert not vf.MISSING
+    assert set(vf.declared_symbols()) == declared        # the binding covers the whole header, nothing more
+
+
+def test_no_device_fails_loudly_not_silently(vf):
+    try:
+        c = vf.Context(0)
+    except vf.B200vfError as e:
+        assert e.status == vf.E_NO_DEVICE                  # CPU box: no fallback path exists
+        assert "no CPU path" in str(e) or "sm_" in str(e)
+    else:
+        c.close()                                          # a GPU box: fine
+
+
+def test_product_never_touches_the_oracle():
+    """a product path that routes through oracle/ would void every parity claim"""
+    pkg = os.path.join(ROOT, "gst-plugins-bad_b200")
+    for dp, _, files in os.walk(pkg):
+        if os.sep + "build" in dp or os.sep + "lib" in dp:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".c", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "import oracle" not in txt and "oracle/" not in txt.replace("the oracle/", ""), os.path.join(dp, f)
+
+
+def px_all():
+    b = np.arange(256, dtype=np.uint32)
+    return b | (b << 8) | (b << 16) | (b << 24)
+
+
+def apply_lut(lut, px):
+    out = np.zeros_like(px)
+    for c in range(4):
+        out |= lut[c][(px >> (8 * c)) & 0xff].astype(np.uint32) << (8 * c)
+    return out
+
+
+def test_lut_builders_match_reference_arithmetic(vf, orc):
+    px = G["px"]
+    for adj in range(0, 257):
+        assert np.array_equal(apply_lut(vf.lut_burn(adj), px_all()), orc.burn(px_all(), adj)), adj
+    assert np.array_equal(apply_lut(vf.lut_dodge(), px), orc.dodge(px))
+    for a, b in [(200, 1), (0, 0), (256, 256), (37, 255), (1, 128)]:
+        assert np.array_equal(apply_lut(vf.lut_chromium(a, b), px), orc.chromium(px, a, b))
+    for t in range(0, 257, 16):
+        for s in range(0, 257, 32):
+            for e in range(0, 257, 32):
+                assert np.array_equal(apply_lut(vf.lut_solarize(t, s, e), px_all()), orc.solarize(px_all(), t, s, e)), (t, s, e)
+    with pytest.raises(vf.B200vfError):
+        vf.lut_burn(257)
+
+
+def test_lut_compose(vf):
+    a, b = vf.lut_burn(100), vf.lut_solarize()
+    c = vf.lut_compose(a, b)
+    px = G["px"]
+    assert np.array_equal(apply_lut(c, px), apply_lut(b, apply_lut(a, px)))
+
+
+def test_gauss_kernel_matches_reference(vf, orc):
+    for s in np.linspace(-20, 20, 81):
+        k, ks = vf.gauss_kernel(float(s))
+        rk, rks = orc.gauss_kernel(float(s))
+        assert np.array_equal(k.view(np.uint32), rk.view(np.uint32)), s
+        assert np.array_equal(ks.view(np.uint32), rks.view(np.uint32)), s
+    with pytest.raises(vf.B200vfError):
+        vf.gauss_kernel(20.5)
+
+
+def test_coloreffects_tables_are_the_reference_tables(vf):
+    gold = oracle.coloreffects_tables()
+    for name, idx in oracle.PRESETS.items():
+        if name != "none":
+            t, ml = vf.coloreffects_table(idx)
+            assert np.array_equal(t, gold[name]) and ml == oracle.PRESET_MAP_LUMA[name]
+
+
+def test_geometric_maps_match_golden(vf):
+    w, h = 16, 12
+    for el, plist in refprops.CASES.items():
+        for i, props in enumerate(plist):
+            m = vf.gt_build_map(el, w, h, props)
+            g = G["gt_map_%s_%d" % (el, i)]
+            same = (m.view(np.uint64) == g.view(np.uint64)) | (np.isnan(m) & np.isnan(g))
+            assert same.all(), (el, props)
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="needs oracle/_ref")
+def test_geometric_maps_match_reference_larger(vf):
+    R = oracle.get("reference")
+    for el, plist in refprops.CASES.items():
+        for props in plist:
+            for (w, h) in [(64, 48), (100, 75)]:
+                m = vf.gt_build_map(el, w, h, props)
+                r = R.gt_map(el, w, h, refprops.full(el, props))
+                assert ((m.view(np.uint64) == r.view(np.uint64)) | (np.isnan(m) & np.isnan(r))).all(), (el, props, w, h)
+
+
+def test_resolve_map_is_do_map(vf, orc):
+    """index table + a numpy gather == the oracle's per-pixel do_map loop, all three off-edge policies"""
+    w, h = 16, 12
+    src = G["gt_src"]
+    for el in refprops.CASES:
+        m = G["gt_map_%s_0" % el]
+        for oe, code in oracle.OFF_EDGE.items():
+            idx = vf.gt_resolve_map(m, w, h, code)
+            px = src.reshape(h * w, 4)
+            out = np.where((idx.reshape(-1) >= 0)[:, None], px[np.maximum(idx.reshape(-1), 0)], 0).astype(np.uint8)
+            assert np.array_equal(out.reshape(h, 4 * w), G["gt_out_%s_%s" % (el, oe)]), (el, oe)
+    # the tunnel centre pixel divides 0/0: it must stay unmapped (-1)
+    m = vf.gt_build_map("tunnel", 64, 48)
+    assert np.isnan(m[24, 32]).all() and vf.gt_resolve_map(m, 64, 48, 1)[24, 32] == -1
+
+
+def test_unknown_element_and_property(vf):
+    with pytest.raises(vf.B200vfError) as e:
+        vf.gt_build_map("diffuse", 8, 8)
+    assert e.value.status == vf.E_UNSUPPORTED
+    with pytest.raises(vf.B200vfError) as e:
+        vf.gt_build_map("bulge", 8, 8, {"nope": 1})
+    assert e.value.status == vf.E_PROPERTY
+
+
+def test_shard_rows_partition(vf):
+    for h in [480, 2160, 4320, 2161, 1080]:
+        for n in [1, 2, 4, 8]:
+            cover = 0
+            for r in range(n):
+                r0, rows = vf.shard_rows(h, r, n)
+                assert r0 == cover and r0 % 2 == 0 and rows >= 4
+                cover += rows
+            assert cover == h
+    with pytest.raises(vf.B200vfError):
+        vf.shard_rows(16, 0, 8)
+
+
+def _num(s):
+    if s is None:
+        return None
+    s = str(s).split(" ")[0]
+    return float(s)
+
+
+def test_element_surface_matches_reference_api_dump(vf):
+    """Factory names, property names, ranges and defaults == docs/plugins/gst_plugins_cache.json of the
+    reference (fixture extracted by tests/golden/make_golden.py); pad-template formats too."""
+    surf = json.load(open(os.path.join(ROOT, "tests", "golden", "element_surface.json")))
+    for name, el in surf.items():
+        if name == "diffuse":
+            with pytest.raises(vf.B200vfError):
+                vf.Element(None, name)
+            continue
+        e = vf.Element(None, name)                          # no device needed to inspect an element
+        for pn, pd in el["properties"].items():
+            if pd["type"] == "GValueArray":                 # perspective's 3x3 matrix: exposed as matrix-0..8
+                assert [e.get_property("matrix-%d" % i) for i in range(9)] == [1, 0, 0, 0, 1, 0, 0, 0, 1]
+                continue
+            got = e.get_property(pn)
+            d = pd.get("default")
+            if d in ("true", "false"):
+                assert got == (1.0 if d == "true" else 0.0), (name, pn)
+            elif "(" in str(d):                             # enum: "none (0)"
+                nick, val = str(d).split(" (")
+                assert got == float(val.rstrip(")")), (name, pn)
+                e.set_property(pn, nick)                    # the nick round-trips
+                assert e.get_property(pn) == got
+            else:
+                assert got == pytest.approx(_num(d), rel=2e-6), (name, pn, got, d)   # the dump prints 6 significant digits
+        for pn, pd in el["properties"].items():            # ranges in a second pass (marble's turbulence aliases y-scale)
+            if pd["type"] == "GValueArray":
+                continue
+            lo, hi = _num(pd.get("min")), _num(pd.get("max"))
+            if lo is not None and lo > -1e300:
+                e.set_property(pn, lo)
+                if pd["type"] in ("guint", "gint") or lo > 0:
+                    with pytest.raises(vf.B200vfError):
+                        e.set_property(pn, lo - 1)
+            if hi is not None and hi < 1e300 and hi < 2147483647:
+                e.set_property(pn, hi)
+                with pytest.raises(vf.B200vfError):
+                    e.set_property(pn, hi + 1)
+        # pad-template formats: every format the reference lists negotiates, an unlisted one does not
+        caps = el["pad-templates"]["sink"]
+        fmts = re.findall(r"format: \{ ([^}]*) \}", caps) or re.findall(r"format: (\w+)", caps)
+        fmts = [f.strip() for f in fmts[0].split(",")] if fmts and "," in fmts[0] else fmts
+        if name == "bayer2rgb":
+            src_fmts = [f.strip() for f in re.findall(r"format: \{ ([^}]*) \}", el["pad-templates"]["src"])[0].split(",")]
+            for f in fmts:
+                for o in src_fmts:
+                    e.set_caps(f, o, 64, 48)
+                    assert e.unit_size() == (64 * 48, 64 * 48 * 4)
+            with pytest.raises(vf.B200vfError):
+                e.set_caps("bggr", "RGB", 64, 48)
+        elif name == "rgb2bayer":
+            e.set_caps("ARGB", "rggb", 63, 48)
+            assert e.unit_size() == (63 * 48 * 4, 64 * 48)
+        else:
+            for f in fmts:
+                e.set_caps(f, f, 33, 17)
+            with pytest.raises(vf.B200vfError):
+                e.set_caps("I420", "I420", 32, 16)
+        e.close()
+
+
+def test_element_without_device_cannot_transform(vf):
+    e = vf.Element(None, "burn")
+    e.set_caps("BGRx", "BGRx", 8, 8)
+    with pytest.raises(vf.B200vfError) as err:
+        e.transform(np.zeros(8 * 8 * 4, np.uint8))
+    assert err.value.status == vf.E_NO_DEVICE
