@@ -19,6 +19,9 @@
 // 16-byte aligned. Everything else goes to bayer2rgb_direct.
 #include "bayer.cuh"
 #include <cuda.h>
+#include <stdlib.h>
+
+int b200vf_next_tile_counter (b200vf_ctx *ctx, cudaStream_t s, unsigned int **out);
 
 namespace {
 
@@ -121,10 +124,16 @@ __device__ __forceinline__ void strip_fast (const uint8_t *rp /* box row of glob
   }
 }
 
+// Warp-specialised persistent kernel. Warp 8 is the producer: it draws tile numbers from a global
+// counter (dynamic scheduling: CTAs that run on a slower SM / die simply take fewer tiles), publishes
+// them through shared memory and issues the TMA box loads up to STAGES tiles ahead, gated by per-stage
+// `empty` mbarriers. Warps 0-7 are consumers: each waits on the stage's `full` mbarrier, processes its
+// own 8-row x 128-px strip and arrives on `empty` - no CTA-wide barrier anywhere in the loop, so a warp
+// that finishes early starts the next tile while its siblings are still storing.
 template <int ORDER, int MODE>
-__global__ void __launch_bounds__ (TMA_THREADS)
+__global__ void __launch_bounds__ (TMA_THREADS + 32)
 bayer2rgb_tma_kernel (const __grid_constant__ CUtensorMap src_map, const TmaParams p,
-    const __grid_constant__ BayerEpilogue epi)
+    const __grid_constant__ BayerEpilogue epi, unsigned int *tile_counter)
 {
   extern __shared__ __align__ (128) uint8_t smem_raw[];
   uint8_t *stage_base = smem_raw;
@@ -132,42 +141,53 @@ bayer2rgb_tma_kernel (const __grid_constant__ CUtensorMap src_map, const TmaPara
   if (MODE != 0) lut_fill (epi_tab, epi.table);
   const uint32_t *tl = epi_tab + (threadIdx.x & 31);
   __shared__ __align__ (8) uint64_t full[STAGES];
+  __shared__ __align__ (8) uint64_t empty[STAGES];
+  __shared__ int tile_of[STAGES];
 
   const int ntiles = p.tiles_x * p.tiles_y * p.nframes;
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) mbar_init (&full[s], 1);
+    for (int s = 0; s < STAGES; s++) { mbar_init (&full[s], 1); mbar_init (&empty[s], TMA_THREADS / 32); }
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads ();
 
-  auto issue = [&] (int t, int s) {
-    int f, ty, tx;
-    tile_coords (t, p, f, ty, tx);
-    mbar_expect_tx (&full[s], BOX_W * BOX_H);
-    // x in 32-bit words: the box starts 16 B left of the tile and one row above it
-    tma_load_3d (stage_base + s * STAGE_BYTES, &src_map, &full[s], tx * (TILE_W / 4) - 4,
-        p.row0 + ty * TILE_H - 1 - p.buf_row0, f);
-  };
+  const int warp = tid >> 5, lane = tid & 31;
 
-  if (tid == 0) {
-#pragma unroll 1
-    for (int s = 0; s < STAGES; s++) {
-      int t = blockIdx.x + s * gridDim.x;
-      if (t < ntiles) issue (t, s);
+  if (warp == TMA_THREADS / 32) {
+    // ------------------------------------------------------------------ producer warp
+    if (lane == 0) {
+      for (int k = 0;; k++) {
+        const int s = k % STAGES;
+        if (k >= STAGES) mbar_wait (&empty[s], ((k / STAGES) - 1) & 1);     // all 8 consumer warps left this stage
+        const int t = (int) atomicAdd (tile_counter, 1u);
+        tile_of[s] = t < ntiles ? t : -1;                                  // -1: no more work
+        if (t >= ntiles) {
+          asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (&full[s])) : "memory");
+          break;
+        }
+        int f, ty, tx;
+        tile_coords (t, p, f, ty, tx);
+        mbar_expect_tx (&full[s], BOX_W * BOX_H);
+        // x in 32-bit words: the box starts 16 B left of the tile and one row above it
+        tma_load_3d (stage_base + s * STAGE_BYTES, &src_map, &full[s], tx * (TILE_W / 4) - 4,
+            p.row0 + ty * TILE_H - 1 - p.buf_row0, f);
+      }
     }
+    return;
   }
 
-  const int warp = tid >> 5, lane = tid & 31;
+  // -------------------------------------------------------------------- consumer warps
   const int half = warp & 1, strip = warp >> 1;
   const int xl = half * 128 + lane * 4;             // pixel x inside the tile
   const int h = p.full_height, w = p.width;
   const int row_end = p.row0 + p.rows;
 
-  int k = 0;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, k++) {
+  for (int k = 0;; k++) {
     const int s = k % STAGES;
-    const uint32_t parity = (k / STAGES) & 1;
+    mbar_wait (&full[s], (k / STAGES) & 1);         // the tile number (and its box) have landed
+    const int t = tile_of[s];
+    if (t < 0) break;
     int f, ty, tx;
     tile_coords (t, p, f, ty, tx);
     const int x0 = tx * TILE_W + xl;
@@ -180,8 +200,6 @@ bayer2rgb_tma_kernel (const __grid_constant__ CUtensorMap src_map, const TmaPara
     const uint8_t *box = stage_base + s * STAGE_BYTES + 16 + xl;     // box row r = global row y0 - 1 + r
     uint8_t *o = p.dst + (size_t) f * p.dst_frame_stride + (size_t) (j0 - p.row0) * p.dst_stride + (size_t) x0 * 4;
     const int fig = (p.first_is_gr ^ j0) & 1;       // role of the strip's first row: 0 = "bg", 1 = "gr"
-
-    mbar_wait (&full[s], parity);
 
     // rows j0-1 .. j0+STRIP are ordinary frame rows (no top mirror, no bottom rule, nothing clipped)
     const bool plain = (j0 >= 1) && (j0 + STRIP < h) && (j0 + STRIP <= row_end);
@@ -216,11 +234,8 @@ bayer2rgb_tma_kernel (const __grid_constant__ CUtensorMap src_map, const TmaPara
         c = d;
       }
     }
-    __syncthreads ();                      // every warp is done reading stage s
-    if (tid == 0) {
-      int tn = t + STAGES * gridDim.x;
-      if (tn < ntiles) issue (tn, s);
-    }
+    __syncwarp ();                                  // every lane is done reading stage s
+    if (lane == 0) asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (&empty[s])) : "memory");
   }
 }
 
@@ -250,9 +265,14 @@ int launch_tma_mode (b200vf_ctx *ctx, const CUtensorMap &map, const TmaParams &p
     attr_set = true;
   }
   int ntiles = p.tiles_x * p.tiles_y * p.nframes;
-  int grid = ctx->sm_count * (MODE ? 3 : 4);   // resident CTAs per SM: 39 KB (+32 KB table) of smem, 256 threads each
+  int per_sm = 2;                              // CTAs per SM (measured sweep 1..6 in profiles/: 2 is best; more CTAs only add DRAM page conflicts)
+  if (const char *e = getenv ("B200VF_TMA_CTAS_PER_SM")) { int v = atoi (e); if (v >= 1 && v <= 8) per_sm = v; }   // tuning knob
+  int grid = ctx->sm_count * per_sm;
   if (grid > ntiles) grid = ntiles;
-  bayer2rgb_tma_kernel<ORDER, MODE><<<grid, TMA_THREADS, smem, s>>> (map, p, epi);
+  unsigned int *counter = nullptr;
+  int rc = b200vf_next_tile_counter (ctx, s, &counter);
+  if (rc) return rc;
+  bayer2rgb_tma_kernel<ORDER, MODE><<<grid, TMA_THREADS + 32, smem, s>>> (map, p, epi, counter);
   return b200vf_launched (ctx, MODE ? "bayer2rgb_tma_fused" : "bayer2rgb_tma");
 }
 template <int ORDER>

@@ -63,21 +63,27 @@ exclusion_kernel (const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t
 // gst/gaudieffects/gstdilate.c:258-345: best of {self, down, right, left} by luminance
 // 90 r + 115 g + 51 b, strict compare in that order (`up` is dead code, :291-294).
 __device__ __forceinline__ uint32_t dil_lum (uint32_t in) {
-  return 90u * ((in >> 16) & 0xff) + 115u * ((in >> 8) & 0xff) + 51u * (in & 0xff);
+  return __dp4a (in, 0x005a7333u, 0u);          // 51*b0 + 115*b1 + 90*b2 (+ 0*x): one IDP4A
 }
-__device__ __forceinline__ void dil_pick (uint32_t &best, uint32_t &bl, uint32_t cand, uint32_t cl, bool erode) {
-  bool take = erode ? (cl < bl) : (cl > bl);
+template <bool ERODE>
+__device__ __forceinline__ void dil_pick_t (uint32_t &best, uint32_t &bl, uint32_t cand, uint32_t cl) {
+  const bool take = ERODE ? (cl < bl) : (cl > bl);
   best = take ? cand : best;
   bl = take ? cl : bl;
+}
+__device__ __forceinline__ void dil_pick (uint32_t &best, uint32_t &bl, uint32_t cand, uint32_t cl, bool erode) {
+  if (erode) dil_pick_t<true> (best, bl, cand, cl); else dil_pick_t<false> (best, bl, cand, cl);
 }
 
 constexpr int DIL_ROWS = 16;   // rows one warp marches down
 
 // width % 4 == 0: a lane owns 4 pixels (one 128-bit word) per row, a warp 128 pixels;
-// left/right neighbours by shuffle, the row below is the next iteration's row.
+// left/right neighbours by shuffle, the row below is the next iteration's row; every
+// pixel's luminance is computed once per row it takes part in (own row, and as `down`).
+template <bool ERODE>
 __global__ void __launch_bounds__ (256)
 dilate_kernel (const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
-    size_t frame_stride, int erode, const uint8_t *__restrict__ below)
+    size_t frame_stride, const uint8_t *__restrict__ below)
 {
   const int lane = threadIdx.x;
   const int x0 = (blockIdx.x * 32 + lane) * 4;
@@ -85,47 +91,50 @@ dilate_kernel (const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w
   if (j0 >= height) return;
   const int jend = min (j0 + DIL_ROWS, height);
   const bool active = x0 < width;
+  const bool last_word = x0 + 4 >= width;
   const size_t rs = (size_t) width * 4;
   const uint8_t *s = src + (size_t) blockIdx.z * frame_stride;
   uint8_t *d = dst + (size_t) blockIdx.z * frame_stride;
   const uint8_t *bel = below ? below + (size_t) blockIdx.z * rs : nullptr;
 
   auto load = [&] (int j, uint4 &px, uint32_t &le, uint32_t &re) {
-    // row `height` = the row under the shard (or absent)
-    const uint8_t *rp = (j < height) ? s + (size_t) j * rs : bel;
+    const uint8_t *rp = (j < height) ? s + (size_t) j * rs : bel;      // row `height` = the row under the shard
     px = make_uint4 (0, 0, 0, 0); le = re = 0;
     if (active) {
       px = ld_stream_v4 (rp + (size_t) x0 * 4);
       if (lane == 0 && x0 > 0) le = ldg_u32 (rp + (size_t) (x0 - 1) * 4);
-      if ((lane == 31 || x0 + 4 >= width) && x0 + 4 < width) re = ldg_u32 (rp + (size_t) (x0 + 4) * 4);
+      if (lane == 31 && !last_word) re = ldg_u32 (rp + (size_t) (x0 + 4) * 4);
     }
   };
 
-  uint4 cur, nxt; uint32_t cle, cre, nle, nre;
+  uint4 cur, nxt; uint32_t cle, cre, nle = 0, nre = 0;
   load (j0, cur, cle, cre);
+  uint32_t cl[4] = { dil_lum (cur.x), dil_lum (cur.y), dil_lum (cur.z), dil_lum (cur.w) };
   for (int j = j0; j < jend; j++) {
     const bool has_down = (j + 1 < height) || (bel != nullptr);
-    if (has_down) load (j + 1, nxt, nle, nre); else { nxt = cur; }
-    uint32_t p[4] = { cur.x, cur.y, cur.z, cur.w };
-    uint32_t dn[4] = { nxt.x, nxt.y, nxt.z, nxt.w };
+    if (has_down) load (j + 1, nxt, nle, nre); else nxt = cur;
+    const uint32_t p[4] = { cur.x, cur.y, cur.z, cur.w };
+    const uint32_t dn[4] = { nxt.x, nxt.y, nxt.z, nxt.w };
+    const uint32_t nl[4] = { dil_lum (nxt.x), dil_lum (nxt.y), dil_lum (nxt.z), dil_lum (nxt.w) };
     uint32_t left_in = __shfl_up_sync (0xffffffffu, cur.w, 1);
     uint32_t right_in = __shfl_down_sync (0xffffffffu, cur.x, 1);
     if (lane == 0) left_in = (x0 > 0) ? cle : cur.x;              // left of column 0 is the pixel itself
-    if (x0 + 4 >= width) right_in = cur.w;                         // right of the last column is itself
+    if (last_word) right_in = cur.w;                               // right of the last column is itself
     else if (lane == 31) right_in = cre;
+    const uint32_t ll = dil_lum (left_in), rl = dil_lum (right_in);
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      uint32_t best = p[k], bl = dil_lum (p[k]);
-      uint32_t rgt = (k < 3) ? p[k + 1] : right_in;
-      uint32_t lft = (k > 0) ? p[k - 1] : left_in;
-      dil_pick (best, bl, dn[k], dil_lum (dn[k]), erode);
-      dil_pick (best, bl, rgt, dil_lum (rgt), erode);
-      dil_pick (best, bl, lft, dil_lum (lft), erode);
+      uint32_t best = p[k], bl = cl[k];
+      dil_pick_t<ERODE> (best, bl, dn[k], nl[k]);                                   // down
+      dil_pick_t<ERODE> (best, bl, (k < 3) ? p[k + 1] : right_in, (k < 3) ? cl[k + 1] : rl);   // right
+      dil_pick_t<ERODE> (best, bl, (k > 0) ? p[k - 1] : left_in, (k > 0) ? cl[k - 1] : ll);    // left (`up` is dead code)
       o[k] = best;
     }
     if (active) st_stream_v4 (d + (size_t) j * rs + (size_t) x0 * 4, make_uint4 (o[0], o[1], o[2], o[3]));
     cur = nxt; cle = nle; cre = nre;
+#pragma unroll
+    for (int k = 0; k < 4; k++) cl[k] = nl[k];
   }
 }
 
@@ -399,7 +408,8 @@ B200VF_API int b200vf_dilate (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_
     dim3 block (32, 8);
     int strips = (height + DIL_ROWS - 1) / DIL_ROWS;
     dim3 grid ((width + 127) / 128, (strips + 7) / 8, nframes);
-    dilate_kernel<<<grid, block, 0, s>>> (d_src, d_dst, width, height, frame_stride, erode, d_below);
+    if (erode) dilate_kernel<true><<<grid, block, 0, s>>> (d_src, d_dst, width, height, frame_stride, d_below);
+    else dilate_kernel<false><<<grid, block, 0, s>>> (d_src, d_dst, width, height, frame_stride, d_below);
     return b200vf_launched (ctx, "dilate");
   }
   dim3 grid ((width + 255) / 256, height, nframes);

@@ -20,6 +20,8 @@ struct b200vf_ctx {
   const char *last_kernel = "";
   int variant = 0;                 // 0 auto, 1 direct, 2 tma
   void *tma_encode = nullptr;      // cuTensorMapEncodeTiled entry point (driver API via cudart)
+  unsigned int *tile_counters = nullptr;   // ring of work counters for dynamically scheduled kernels
+  unsigned int tile_counter_next = 0;
 };
 
 void b200vf_set_error (const char *fmt, ...);

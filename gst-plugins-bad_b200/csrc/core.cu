@@ -72,6 +72,7 @@ B200VF_API void b200vf_ctx_destroy (b200vf_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice (ctx->device);
   if (ctx->stream) cudaStreamDestroy (ctx->stream);
+  if (ctx->tile_counters) cudaFree (ctx->tile_counters);
   delete ctx;
 }
 B200VF_API int b200vf_ctx_device (const b200vf_ctx *ctx) { return ctx ? ctx->device : -1; }
@@ -229,5 +230,19 @@ B200VF_API int b200vf_pool_download (b200vf_pool *pool, int i, void *host_dst, s
       "pool_download: bad argument");
   B200VF_CHECK_CUDA (cudaMemcpyAsync (host_dst, pool->d_base + pool->pitch * i, bytes, cudaMemcpyDeviceToHost,
       b200vf_stream (pool->ctx, stream)));
+  return B200VF_OK;
+}
+
+// Work counters for dynamically scheduled persistent kernels: a ring of 256 counters, each zeroed
+// on the launching stream right before its launch (stream-ordered, so launches on the same stream
+// never share a live counter; 256 in-flight launches across streams would be needed to collide).
+int b200vf_next_tile_counter (b200vf_ctx *ctx, cudaStream_t s, unsigned int **out) {
+  const unsigned ring = 256;
+  if (!ctx->tile_counters) {
+    B200VF_CHECK_CUDA (cudaMalloc ((void **) &ctx->tile_counters, ring * sizeof (unsigned int)));
+  }
+  unsigned int *c = ctx->tile_counters + (ctx->tile_counter_next++ % ring);
+  B200VF_CHECK_CUDA (cudaMemsetAsync (c, 0, sizeof (unsigned int), s));
+  *out = c;
   return B200VF_OK;
 }

@@ -17,6 +17,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <thread>
 
 namespace {
 
@@ -348,9 +349,24 @@ B200VF_API int b200vf_gt_build_map (const char *element, int width, int height, 
       s.cos_table[i] = s.get ("y-scale") * cos (angle);
     }
   }
-  double *ptr = map_xy;
-  for (int y = 0; y < height; y++)
-    for (int x = 0; x < width; x++, ptr += 2) def->fn (s, x, y, ptr, ptr + 1);
+  // every pixel is independent: rows are split over the host cores (the reference builds its map
+  // on one thread under the object lock, 3.6 s at 8K; the values do not depend on the split)
+  unsigned nthreads = std::thread::hardware_concurrency ();
+  if (nthreads > 32) nthreads = 32;
+  if (nthreads < 1 || (long long) width * height < (1 << 18)) nthreads = 1;
+  auto rows = [&] (int y0, int y1) {
+    for (int y = y0; y < y1; y++) {
+      double *ptr = map_xy + (size_t) y * width * 2;
+      for (int x = 0; x < width; x++, ptr += 2) def->fn (s, x, y, ptr, ptr + 1);
+    }
+  };
+  if (nthreads == 1) rows (0, height);
+  else {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nthreads; t++)
+      pool.emplace_back (rows, (int) ((long long) height * t / nthreads), (int) ((long long) height * (t + 1) / nthreads));
+    for (auto &th : pool) th.join ();
+  }
   delete noise;
   return B200VF_OK;
 }

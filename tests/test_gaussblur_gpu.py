@@ -27,6 +27,19 @@ def test_sigmas_small_frames(ctx, vf, orc, rng, sigma, p0):
         assert np.array_equal(got, want), (sigma, p0, w, h, ctx.last_kernel(), np.abs(got.astype(int) - want).max(), np.argwhere(got != want)[:4])
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_many_random_pixels_are_bit_exact(ctx, vf, orc, seed):
+    """Separate multiply/add vs a fused multiply-add differ in well under 1 % of the output bytes, so
+    small frames can hide a contraction; 3 x 31k pixels x 3 sigmas make it visible."""
+    rng = np.random.default_rng(seed)
+    w, h = 192, 160
+    fr = frames.random_u8(rng, h, 4 * w)
+    for sigma, p0 in [(1.2, 1), (2.0, 0), (5.0, 1)]:
+        got = run(ctx, vf, fr, w, h, sigma, p0)
+        want = orc.gaussblur(fr, w, h, sigma, p0)
+        assert np.array_equal(got, want), (sigma, p0, int((got != want).sum()), np.argwhere(got != want)[:4])
+
+
 def test_kernel_taps_match_reference(vf, orc):
     for sigma in [-20, -5, -1.2, 0, 0.3, 1.2, 2.0, 5, 12.5, 20]:
         k, ks = vf.gauss_kernel(sigma)

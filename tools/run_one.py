@@ -1,0 +1,32 @@
+"""Runs one element kernel a few times (for ncu -k regex:... captures of kernels bench.py --profile does not reach).
+   python tools/run_one.py gaussblur|dilate|exclusion|chromahold|remap|lut4|direct [4k|8k]"""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gst-plugins-bad_b200"))
+import torch, b200vf
+what = sys.argv[1]; size = sys.argv[2] if len(sys.argv) > 2 else "4k"
+w, h = (3840, 2160) if size == "4k" else (7680, 4320)
+ctx = b200vf.Context(0); side = torch.cuda.Stream(); torch.cuda.set_stream(side); st = side.cuda_stream
+n = 2
+a = torch.randint(0, 255, (n, h, 4 * w), dtype=torch.uint8, device="cuda"); b = torch.empty_like(a)
+if what == "gaussblur":
+    k, ks = b200vf.gauss_kernel(5.0)
+    f = lambda: ctx.gaussblur(a, b, w, h, 4 * w, 1, k, ks, exact=True, nframes=n, stream=st)
+elif what == "dilate":
+    f = lambda: ctx.dilate(a, b, w, h, False, nframes=n, stream=st)
+elif what == "exclusion":
+    f = lambda: ctx.exclusion(a, b, n * w * h, 175, stream=st)
+elif what == "chromahold":
+    f = lambda: ctx.chromahold(a, w, h, 4 * w, (0, 1, 2), (255, 0, 0), 30, nframes=n, stream=st)
+elif what == "lut4":
+    lut = b200vf.lut_burn(175); f = lambda: ctx.lut4(a, b, n * w * h, lut, stream=st)
+elif what == "remap":
+    idx = torch.from_numpy(b200vf.gt_resolve_map(b200vf.gt_build_map("fisheye", w, h), w, h, 1)).cuda()
+    f = lambda: ctx.remap(a, b, idx, w, h, 4, 4 * w, nframes=n, stream=st)
+elif what == "direct":
+    src = torch.randint(0, 255, (8, h, w), dtype=torch.uint8, device="cuda"); dst = torch.empty((8, h, 4 * w), dtype=torch.uint8, device="cuda")
+    ctx.set_variant("direct"); f = lambda: ctx.bayer2rgb(src, w, dst, 4 * w, w, h, 0, (0, 1, 2), nframes=8, stream=st)
+for _ in range(3):
+    f()
+torch.cuda.synchronize()
+print("ran", what, ctx.last_kernel())
