@@ -252,16 +252,17 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
-    # keep the GPU under the same load a little longer so the 50 ms clock sampler sees it (untimed)
-    t_probe = time.perf_counter()
-    while time.perf_counter() - t_probe < 1.0 and rank == 0 and not args.profile:
-        step()
-        torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
     tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = float(tt.item())
+    # keep the GPU under the same load ~1 s longer so the 50 ms clock sampler sees it (untimed; every
+    # rank runs the same number of steps: the N>1 step contains a collective)
+    if not args.profile:
+        for _ in range(min(3000, int(1000.0 / max(ms / args.steps, 1e-3)) + 1)):
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
     ms_per_step = ms / args.steps
     fps = nfr * args.steps / (ms * 1e-3)
 
