@@ -33,6 +33,9 @@ sys.path.insert(0, os.path.join(ROOT, "gst-plugins-bad_b200"))
 W4K, H4K = 3840, 2160
 METRIC = "bayer2rgb frames/s (3840x2160 bggr->RGBA)"
 FALLBACK_HBM_GBS = 6650.0
+# dram__bytes_read.sum + dram__bytes_write.sum of bayer2rgb_tma per 4K frame, from the committed ncu capture
+# profiles/r01_bayer2rgb_tma_final.md (938.2 MB for a 24-frame launch; algorithmic 41.47 MB/frame)
+NCU_TRAFFIC_BYTES_PER_FRAME = 938.21056e6 / 24
 
 
 def hbm_peak():
@@ -317,7 +320,8 @@ def main():
                    "l2": "inputs+outputs per step = %.1f GB per GPU, far larger than L2 (no flush needed)" % (
                        px_per_launch * 5 / 1e9)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_kind": peak_kind,
+                     "traffic": NCU_TRAFFIC_BYTES_PER_FRAME * (px_per_launch / (w * h)), "traffic_unit": "bytes per launch "
+                     "(ncu dram read+write of the committed capture, scaled by frames per launch)", "peak_kind": peak_kind,
                      "note": "5 algorithmic B/px x pixels per launch / CUDA-event launch time; at N>1 the step also "
                              "contains the halo exchange"},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": Be * w * h * world,
@@ -413,8 +417,12 @@ def side_measurements(ctx, torch, b200vf, st, side, peak):
         for exact in (1, 0):
             t = timeit(lambda: ctx.gaussblur(a, b, w, h, 4 * w, 1, k, ks, exact=bool(exact), nframes=ng, stream=st), iters=3)
             flops = 16 * len(k) * px * ng
+            # FP32 roofline: 148 SMs x 128 lanes x 1.965 GHz = 37.2 T lane-op/s; packed f32x2 ops issue at half
+            # rate on B200 (measured, tools/probe/fp_probe.cu), so they do not raise it. exact = mul + add per tap.
+            fp32_peak = 148 * 128 * 1.965e9
             rec("gaussblur_sigma5_%s_%s" % (tag, "exact" if exact else "fma"), ng, px, 8, t,
-                {"fp32_ops_per_s": flops / t, "bound": "fp32 issue, not HBM (SURVEY D6)"})
+                {"fp32_ops_per_s": flops / t, "frac_fp32": (flops if exact else flops / 2) / t / fp32_peak,
+                 "bound": "fp32 issue, not HBM (SURVEY D6)"})
         if tag == "8k":
             # BASELINE.json configs[3]: fisheye 7680x4320 RGBA (nearest-neighbour gather, index table)
             t0 = time.perf_counter()

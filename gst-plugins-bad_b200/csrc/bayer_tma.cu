@@ -256,6 +256,26 @@ EncodeTiledFn get_encode (b200vf_ctx *ctx) {
   return (EncodeTiledFn) ctx->tma_encode;
 }
 
+}  // namespace
+
+// Shared by the other TMA users (gaussblur): a 3-D tensor of 32-bit words (x, y, frame).
+int b200vf_encode_u32_3d (b200vf_ctx *ctx, CUtensorMap *map, const void *base, uint64_t words_x, uint64_t rows,
+    uint64_t frames, uint64_t row_pitch_bytes, uint64_t frame_pitch_bytes, uint32_t box_x, uint32_t box_y) {
+  EncodeTiledFn encode = get_encode (ctx);
+  B200VF_REQUIRE (encode, B200VF_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[3] = { words_x, rows, frames };
+  cuuint64_t gstride[2] = { row_pitch_bytes, frames > 1 ? frame_pitch_bytes : row_pitch_bytes * rows };
+  cuuint32_t box[3] = { box_x, box_y, 1 };
+  cuuint32_t estr[3] = { 1, 1, 1 };
+  CUresult r = encode (map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *) base, gdim, gstride, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200VF_REQUIRE (r == CUDA_SUCCESS, B200VF_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int) r);
+  return B200VF_OK;
+}
+
+namespace {
+
 template <int ORDER, int MODE>
 int launch_tma_mode (b200vf_ctx *ctx, const CUtensorMap &map, const TmaParams &p, const BayerEpilogue &epi, cudaStream_t s) {
   static bool attr_set = false;
