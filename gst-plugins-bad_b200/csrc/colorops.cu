@@ -50,7 +50,21 @@ exclusion_kernel (const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t
   table_fill (tab, p.t);
   const uint32_t *tl = tab + (threadIdx.x & 31);
   const size_t stride = (size_t) gridDim.x * blockDim.x;
-  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+  constexpr int U = 4;                                     // 128-bit groups in flight per thread
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < n16; i += U * stride) {
+    uint4 v[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) v[k] = ld_stream_v4 (src + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      uint4 o;
+      o.x = excl_px (tl, v[k].x, p.magic, p.factor); o.y = excl_px (tl, v[k].y, p.magic, p.factor);
+      o.z = excl_px (tl, v[k].z, p.magic, p.factor); o.w = excl_px (tl, v[k].w, p.magic, p.factor);
+      st_stream_v4 (dst + i + k * stride, o);
+    }
+  }
+  for (; i < n16; i += stride) {
     uint4 v = ld_stream_v4 (src + i), o;
     o.x = excl_px (tl, v.x, p.magic, p.factor); o.y = excl_px (tl, v.y, p.magic, p.factor);
     o.z = excl_px (tl, v.z, p.magic, p.factor); o.w = excl_px (tl, v.w, p.magic, p.factor);
@@ -213,7 +227,26 @@ coloreffects4_kernel (uint8_t *data, int width, int height, int row_stride, size
   for (int y = blockIdx.y; y < height; y += gridDim.y) {
     uint8_t *row = data + (size_t) blockIdx.z * frame_stride + (size_t) y * row_stride;
     const bool vec = (((uintptr_t) row) & 15) == 0;
-    for (int gx = blockIdx.x * blockDim.x + threadIdx.x; gx < groups; gx += gridDim.x * blockDim.x) {
+    const int gstride = gridDim.x * blockDim.x;
+    int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int U = 4;                                   // full 128-bit groups in flight per thread
+    if (vec) {
+      const int full = width / 4;
+      uint4 *r4 = reinterpret_cast<uint4 *> (row);
+      for (; gx + (U - 1) * gstride < full; gx += U * gstride) {
+        uint4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) v[k] = ld_na_v4 (r4 + gx + k * gstride);
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+          uint4 o;
+          if (AYUV) { o.x = ce_ayuv_px (tl, v[k].x, p); o.y = ce_ayuv_px (tl, v[k].y, p); o.z = ce_ayuv_px (tl, v[k].z, p); o.w = ce_ayuv_px (tl, v[k].w, p); }
+          else { o.x = ce_rgb_px (tl, v[k].x, p); o.y = ce_rgb_px (tl, v[k].y, p); o.z = ce_rgb_px (tl, v[k].z, p); o.w = ce_rgb_px (tl, v[k].w, p); }
+          st_stream_v4 (r4 + gx + k * gstride, o);
+        }
+      }
+    }
+    for (; gx < groups; gx += gstride) {
       int x0 = gx * 4, n = min (4, width - x0);
       uint32_t *px = reinterpret_cast<uint32_t *> (row) + x0;
       if (vec && n == 4) {
@@ -319,7 +352,25 @@ chromahold_kernel (uint8_t *data, int width, int height, int row_stride, size_t 
   for (int y = blockIdx.y; y < height; y += gridDim.y) {
     uint8_t *row = data + (size_t) blockIdx.z * frame_stride + (size_t) y * row_stride;
     const bool vec = (((uintptr_t) row) & 15) == 0;
-    for (int gx = blockIdx.x * blockDim.x + threadIdx.x; gx < groups; gx += gridDim.x * blockDim.x) {
+    const int gstride = gridDim.x * blockDim.x;
+    int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int U = 4;
+    if (vec) {
+      const int full = width / 4;
+      uint4 *r4 = reinterpret_cast<uint4 *> (row);
+      for (; gx + (U - 1) * gstride < full; gx += U * gstride) {
+        uint4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) v[k] = ld_na_v4 (r4 + gx + k * gstride);
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+          uint4 o;
+          o.x = ch_px (tl, v[k].x, p); o.y = ch_px (tl, v[k].y, p); o.z = ch_px (tl, v[k].z, p); o.w = ch_px (tl, v[k].w, p);
+          st_stream_v4 (r4 + gx + k * gstride, o);
+        }
+      }
+    }
+    for (; gx < groups; gx += gstride) {
       int x0 = gx * 4, n = min (4, width - x0);
       uint32_t *px = reinterpret_cast<uint32_t *> (row) + x0;
       if (vec && n == 4) {

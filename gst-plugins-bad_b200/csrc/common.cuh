@@ -76,6 +76,13 @@ __device__ __forceinline__ uint4 ld_stream_v4 (const void *p) {
       : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+// the same for data this kernel also writes (in-place elements): no .nc, still no L1 allocation
+__device__ __forceinline__ uint4 ld_na_v4 (const void *p) {
+  uint4 r;
+  asm volatile ("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
 __device__ __forceinline__ void st_stream_v4 (void *p, uint4 v) {
   asm volatile ("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
       :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");

@@ -18,7 +18,7 @@
 namespace {
 
 constexpr int LUT_THREADS = 512;
-constexpr int LUT_UNROLL = 2;            // 128-bit groups in flight per thread
+constexpr int LUT_UNROLL = 4;            // 128-bit groups in flight per thread
 
 __global__ void __launch_bounds__ (LUT_THREADS)
 lut4_kernel (const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n16,
