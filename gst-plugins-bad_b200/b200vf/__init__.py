@@ -85,6 +85,11 @@ _SIGS = {
     "b200vf_shard_rows": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "b200vf_comm_halo_exchange": (_i, [_vp, _vp, _sz, _i, _i, _sz, _i, _vp]),
     "b200vf_comm_barrier": (_i, [_vp, _vp]),
+    "b200vf_factory_count": (_i, []),
+    "b200vf_factory_get": (_i, [_i, _vp]),
+    "b200vf_factory_find": (_i, [C.c_char_p, _vp]),
+    "b200vf_factory_property": (_i, [C.c_char_p, _i, _vp]),
+    "b200vf_factory_format": (C.c_char_p, [C.c_char_p, _i]),
     "b200vf_element_factory_make": (_i, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "b200vf_element_destroy": (None, [_vp]),
     "b200vf_element_factory_name": (C.c_char_p, [_vp]),
@@ -358,6 +363,36 @@ def shard_rows(height, rank, nranks):
     r0, r = _i(0), _i(0)
     check(lib.b200vf_shard_rows(height, rank, nranks, C.byref(r0), C.byref(r)))
     return r0.value, r.value
+
+
+class FactoryInfo(C.Structure):
+    _fields_ = [(n, C.c_char_p) for n in ("factory", "plugin", "plugin_description", "plugin_license", "type_name",
+                                           "parent_type_name", "klass", "long_name", "description", "author")] + \
+               [("in_place", _i), ("n_properties", _i), ("n_formats", _i)]
+
+
+class PropertyInfo(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("type", _i), ("min", C.c_double), ("max", C.c_double), ("default", C.c_double),
+                ("controllable", _i), ("n_nicks", _i), ("nicks", C.POINTER(C.c_char_p))]
+
+
+def factories():
+    """{factory: {info..., properties: [...], formats: [...]}} - what gst-inspect would print."""
+    out = {}
+    for i in range(lib.b200vf_factory_count()):
+        fi = FactoryInfo()
+        check(lib.b200vf_factory_get(i, C.byref(fi)))
+        d = {k: (getattr(fi, k).decode() if isinstance(getattr(fi, k), bytes) else getattr(fi, k)) for k, _ in FactoryInfo._fields_}
+        props = []
+        for j in range(fi.n_properties):
+            pi = PropertyInfo()
+            check(lib.b200vf_factory_property(fi.factory, j, C.byref(pi)))
+            props.append({"name": pi.name.decode(), "type": pi.type, "min": pi.min, "max": pi.max, "default": pi.default,
+                          "controllable": bool(pi.controllable), "nicks": [pi.nicks[k].decode() for k in range(pi.n_nicks)]})
+        d["properties"] = props
+        d["formats"] = [lib.b200vf_factory_format(fi.factory, j).decode() for j in range(fi.n_formats)]
+        out[d["factory"]] = d
+    return out
 
 
 class Element:

@@ -1,0 +1,398 @@
+/* gstb200vf.c - GStreamer element shells over libb200vf.so (C/GLib, no per-pixel work).
+ *
+ * One source, compiled once per plugin with -DB200VF_PLUGIN=<bayer|gaudieffects|coloreffects|geometrictransform>
+ * (gst/meson.build), yields libgstbayer.so, libgstgaudieffects.so, libgstcoloreffects.so and
+ * libgstgeometrictransform.so that REPLACE the stock plugins: same plugin names, factory names, GType names and
+ * parents, klass/description strings, GObject properties (names, ranges, defaults, GST_PARAM_CONTROLLABLE) and pad
+ * templates - all taken from the introspection table of the library (b200vf_factory_*), which is generated from and
+ * tested against the reference's own API dump (docs/plugins/gst_plugins_cache.json). The data vfuncs
+ * (GstBaseTransform::transform, gst/bayer/gstbayer2rgb.c:456-487; GstVideoFilter::transform_frame[_ip],
+ * e.g. gst/gaudieffects/gstburn.c:214-250) map the buffers and hand them to b200vf_element_transform_host, i.e. the
+ * sm_100a kernels; start() fails with a GST_ELEMENT_ERROR when there is no sm_100 device (no CPU path), like
+ * sys/nvcodec registers nothing without a driver (sys/nvcodec/plugin.c:72-103).
+ *
+ * NOT compiled in this repository's CI image (no GLib/GStreamer there): build-gated on
+ * `pkg-config gstreamer-video-1.0` in gst/meson.build. The mapping from element state to C-ABI calls is the one
+ * host/elements.cpp exercises on the GPU in tests/test_elements_gpu.py.
+ */
+#ifdef HAVE_CONFIG_H
+#include "config.h"
+#endif
+#include <string.h>
+#include <gst/gst.h>
+#include <gst/base/gstbasetransform.h>
+#include <gst/video/video.h>
+#include <gst/video/gstvideofilter.h>
+#include "b200vf.h"
+
+#ifndef B200VF_PLUGIN
+#error "compile with -DB200VF_PLUGIN=bayer|gaudieffects|coloreffects|geometrictransform"
+#endif
+#define STR_(x) #x
+#define STR(x) STR_(x)
+#ifndef PACKAGE
+#define PACKAGE "gst-plugins-bad"
+#endif
+#ifndef VERSION
+#define VERSION "1.19.2"
+#endif
+
+GST_DEBUG_CATEGORY_STATIC (b200vf_debug);
+#define GST_CAT_DEFAULT b200vf_debug
+
+typedef struct
+{
+  GstVideoFilter parent;        /* GstBaseTransform is its first member: bayer elements use only that part */
+  b200vf_ctx *ctx;
+  b200vf_element *el;
+  gint device;
+} GstB200vf;
+
+typedef struct
+{
+  GstVideoFilterClass parent_class;
+  const gchar *factory;         /* set from class_data */
+} GstB200vfClass;
+
+#define B200VF(obj) ((GstB200vf *) (obj))
+#define B200VF_GET_CLASS(obj) ((GstB200vfClass *) G_OBJECT_GET_CLASS (obj))
+
+enum { PROP_0, PROP_FIRST };    /* property ids: PROP_FIRST + index in the library's table */
+
+static gboolean
+is_bayer_plugin_factory (const gchar * f)
+{
+  return !strcmp (f, "bayer2rgb") || !strcmp (f, "rgb2bayer");
+}
+
+/* ---- properties: straight through to the element mirror (which validates ranges like GParamSpec does) ---- */
+static void
+b200vf_set_property (GObject * object, guint id, const GValue * value, GParamSpec * pspec)
+{
+  GstB200vf *self = B200VF (object);
+  gdouble v = 0;
+  if (G_VALUE_HOLDS_UINT (value)) v = g_value_get_uint (value);
+  else if (G_VALUE_HOLDS_INT (value)) v = g_value_get_int (value);
+  else if (G_VALUE_HOLDS_BOOLEAN (value)) v = g_value_get_boolean (value);
+  else if (G_VALUE_HOLDS_DOUBLE (value)) v = g_value_get_double (value);
+  else if (G_VALUE_HOLDS_ENUM (value)) v = g_value_get_enum (value);
+  GST_OBJECT_LOCK (self);
+  if (b200vf_element_set_property (self->el, pspec->name, v) != B200VF_OK)
+    GST_WARNING_OBJECT (self, "%s", b200vf_last_error ());
+  GST_OBJECT_UNLOCK (self);
+}
+
+static void
+b200vf_get_property (GObject * object, guint id, GValue * value, GParamSpec * pspec)
+{
+  GstB200vf *self = B200VF (object);
+  gdouble v = 0;
+  b200vf_element_get_property (self->el, pspec->name, &v);
+  if (G_VALUE_HOLDS_UINT (value)) g_value_set_uint (value, (guint) v);
+  else if (G_VALUE_HOLDS_INT (value)) g_value_set_int (value, (gint) v);
+  else if (G_VALUE_HOLDS_BOOLEAN (value)) g_value_set_boolean (value, v != 0);
+  else if (G_VALUE_HOLDS_DOUBLE (value)) g_value_set_double (value, v);
+  else if (G_VALUE_HOLDS_ENUM (value)) g_value_set_enum (value, (gint) v);
+}
+
+static GType
+enum_type_for (const gchar * type_name, const b200vf_property_info * p)
+{
+  /* GstColorEffectsPreset, GstMirrorMode, GstGeometricTransformOffEdgesPixelsMethod (reference type names) */
+  const gchar *name = !strcmp (p->name, "preset") ? "GstColorEffectsPreset" :
+      !strcmp (p->name, "mode") ? "GstMirrorMode" : "GstGeometricTransformOffEdgesPixelsMethod";
+  GType t = g_type_from_name (name);
+  if (!t) {
+    GEnumValue *vals = g_new0 (GEnumValue, p->n_nicks + 1);
+    for (gint i = 0; i < p->n_nicks; i++) {
+      vals[i].value = i;
+      vals[i].value_name = p->nicks[i];
+      vals[i].value_nick = p->nicks[i];
+    }
+    t = g_enum_register_static (name, vals);
+  }
+  return t;
+}
+
+/* ---- negotiation ---- */
+static gboolean
+b200vf_configure (GstB200vf * self, const gchar * in_fmt, const gchar * out_fmt, gint w, gint h)
+{
+  if (b200vf_element_set_caps (self->el, in_fmt, out_fmt, w, h) != B200VF_OK) {
+    GST_WARNING_OBJECT (self, "%s", b200vf_last_error ());
+    return FALSE;
+  }
+  return TRUE;
+}
+
+/* GstVideoFilter::set_info (e.g. gstgaussblur.c:162-178, gstgeometrictransform.c:130-165) */
+static gboolean
+b200vf_set_info (GstVideoFilter * vf, GstCaps * incaps, GstVideoInfo * in_info, GstCaps * outcaps, GstVideoInfo * out_info)
+{
+  const gchar *f = gst_video_format_to_string (GST_VIDEO_INFO_FORMAT (in_info));
+  return b200vf_configure (B200VF (vf), f, f, GST_VIDEO_INFO_WIDTH (in_info), GST_VIDEO_INFO_HEIGHT (in_info));
+}
+
+/* bayer2rgb / rgb2bayer: set_caps, transform_caps, get_unit_size (gstbayer2rgb.c:237-352) */
+static gboolean
+b200vf_bayer_set_caps (GstBaseTransform * base, GstCaps * incaps, GstCaps * outcaps)
+{
+  GstStructure *si = gst_caps_get_structure (incaps, 0), *so = gst_caps_get_structure (outcaps, 0);
+  gint w = 0, h = 0;
+  gst_structure_get_int (si, "width", &w);
+  gst_structure_get_int (si, "height", &h);
+  return b200vf_configure (B200VF (base), gst_structure_get_string (si, "format"), gst_structure_get_string (so, "format"), w, h);
+}
+
+static GstCaps *
+b200vf_bayer_transform_caps (GstBaseTransform * base, GstPadDirection direction, GstCaps * caps, GstCaps * filter)
+{
+  const gchar *factory = B200VF_GET_CLASS (base)->factory;
+  gboolean to_raw = (!strcmp (factory, "bayer2rgb")) == (direction == GST_PAD_SINK);
+  GstCaps *res = gst_caps_copy (caps);
+  for (guint i = 0; i < gst_caps_get_size (res); i++) {
+    GstStructure *s = gst_caps_get_structure (res, i);
+    gst_structure_set_name (s, to_raw ? "video/x-raw" : "video/x-bayer");
+    if (to_raw) gst_structure_remove_field (s, "format");
+    else gst_structure_remove_fields (s, "format", "colorimetry", "chroma-site", NULL);
+  }
+  if (filter) {
+    GstCaps *tmp = res;
+    res = gst_caps_intersect_full (filter, tmp, GST_CAPS_INTERSECT_FIRST);
+    gst_caps_unref (tmp);
+  }
+  return res;
+}
+
+static gboolean
+b200vf_bayer_get_unit_size (GstBaseTransform * base, GstCaps * caps, gsize * size)
+{
+  GstStructure *s = gst_caps_get_structure (caps, 0);
+  gint w, h;
+  if (!gst_structure_get_int (s, "width", &w) || !gst_structure_get_int (s, "height", &h)) {
+    GST_ELEMENT_ERROR (base, CORE, NEGOTIATION, (NULL), ("Incomplete caps, some required field missing"));
+    return FALSE;
+  }
+  *size = gst_structure_has_name (s, "video/x-raw") ? (gsize) w * h * 4 : (gsize) GST_ROUND_UP_4 (w) * h;
+  return TRUE;
+}
+
+/* ---- lifecycle ---- */
+static gboolean
+b200vf_start (GstBaseTransform * base)
+{
+  GstB200vf *self = B200VF (base);
+  if (!self->ctx && b200vf_ctx_create (self->device, &self->ctx) != B200VF_OK) {
+    GST_ELEMENT_ERROR (self, LIBRARY, INIT, ("No B200 (sm_100) device: this element has no CPU path"), ("%s", b200vf_last_error ()));
+    return FALSE;
+  }
+  /* re-create the mirror with a device context, carrying the property values over */
+  b200vf_element *old = self->el;
+  if (b200vf_element_factory_make (self->ctx, B200VF_GET_CLASS (self)->factory, &self->el) != B200VF_OK) {
+    self->el = old;
+    return FALSE;
+  }
+  b200vf_factory_info fi;
+  b200vf_factory_find (B200VF_GET_CLASS (self)->factory, &fi);
+  for (gint i = 0; i < fi.n_properties; i++) {
+    b200vf_property_info p;
+    gdouble v;
+    b200vf_factory_property (fi.factory, i, &p);
+    if (b200vf_element_get_property (old, p.name, &v) == B200VF_OK) b200vf_element_set_property (self->el, p.name, v);
+  }
+  b200vf_element_destroy (old);
+  return TRUE;
+}
+
+static gboolean
+b200vf_stop (GstBaseTransform * base)
+{
+  return TRUE;                  /* the index table / staging buffers live with the element mirror */
+}
+
+static void
+b200vf_before_transform (GstBaseTransform * base, GstBuffer * buf)
+{
+  /* GstController: update the properties (gstburn.c:230-240, gstgeometrictransform.c:209-224) */
+  GstClockTime ts = gst_segment_to_stream_time (&base->segment, GST_FORMAT_TIME, GST_BUFFER_TIMESTAMP (buf));
+  if (GST_CLOCK_TIME_IS_VALID (ts)) gst_object_sync_values (GST_OBJECT (base), ts);
+}
+
+/* ---- data ---- */
+static GstFlowReturn
+b200vf_flow (GstB200vf * self, int rc)
+{
+  if (rc == B200VF_OK) return GST_FLOW_OK;
+  if (rc == B200VF_E_NOT_NEGOTIATED) return GST_FLOW_NOT_NEGOTIATED;
+  GST_ELEMENT_ERROR (self, LIBRARY, FAILED, ("b200vf: %s", b200vf_status_string (rc)), ("%s", b200vf_last_error ()));
+  return GST_FLOW_ERROR;
+}
+
+static GstFlowReturn
+b200vf_transform_frame (GstVideoFilter * vf, GstVideoFrame * in, GstVideoFrame * out)
+{
+  return b200vf_flow (B200VF (vf), b200vf_element_transform_host (B200VF (vf)->el,
+          GST_VIDEO_FRAME_PLANE_DATA (in, 0), GST_VIDEO_FRAME_PLANE_DATA (out, 0), 1));
+}
+
+static GstFlowReturn
+b200vf_transform_frame_ip (GstVideoFilter * vf, GstVideoFrame * frame)
+{
+  guint8 *d = GST_VIDEO_FRAME_PLANE_DATA (frame, 0);
+  return b200vf_flow (B200VF (vf), b200vf_element_transform_host (B200VF (vf)->el, d, d, 1));
+}
+
+static GstFlowReturn
+b200vf_bayer_transform (GstBaseTransform * base, GstBuffer * inbuf, GstBuffer * outbuf)
+{
+  GstMapInfo in, out;
+  if (!gst_buffer_map (inbuf, &in, GST_MAP_READ)) goto map_failed;
+  if (!gst_buffer_map (outbuf, &out, GST_MAP_WRITE)) {
+    gst_buffer_unmap (inbuf, &in);
+    goto map_failed;
+  }
+  {
+    int rc = b200vf_element_transform_host (B200VF (base)->el, in.data, out.data, 1);
+    gst_buffer_unmap (outbuf, &out);
+    gst_buffer_unmap (inbuf, &in);
+    return b200vf_flow (B200VF (base), rc);
+  }
+map_failed:
+  GST_WARNING_OBJECT (base, "Could not map buffer, skipping");      /* the reference returns OK here (:484-486) */
+  return GST_FLOW_OK;
+}
+
+/* ---- class / instance init, driven by the introspection table ---- */
+static void
+b200vf_finalize (GObject * object)
+{
+  GstB200vf *self = B200VF (object);
+  if (self->el) b200vf_element_destroy (self->el);
+  if (self->ctx) b200vf_ctx_destroy (self->ctx);
+  G_OBJECT_CLASS (g_type_class_peek_parent (G_OBJECT_GET_CLASS (object)))->finalize (object);
+}
+
+static GstCaps *
+raw_caps_for (const b200vf_factory_info * fi)
+{
+  GString *s = g_string_new ("{ ");
+  for (gint i = 0; i < fi->n_formats; i++) g_string_append_printf (s, "%s%s", i ? ", " : "", b200vf_factory_format (fi->factory, i));
+  g_string_append (s, " }");
+  gchar *c = g_strdup_printf (GST_VIDEO_CAPS_MAKE ("%s"), s->str);
+  GstCaps *caps = gst_caps_from_string (c);
+  g_free (c);
+  g_string_free (s, TRUE);
+  return caps;
+}
+
+static void
+b200vf_class_init (gpointer g_class, gpointer class_data)
+{
+  GstB200vfClass *klass = g_class;
+  GObjectClass *oc = G_OBJECT_CLASS (g_class);
+  GstElementClass *ec = GST_ELEMENT_CLASS (g_class);
+  GstBaseTransformClass *bc = GST_BASE_TRANSFORM_CLASS (g_class);
+  b200vf_factory_info fi;
+  klass->factory = class_data;
+  b200vf_factory_find (klass->factory, &fi);
+
+  oc->set_property = b200vf_set_property;
+  oc->get_property = b200vf_get_property;
+  oc->finalize = b200vf_finalize;
+  gst_element_class_set_static_metadata (ec, fi.long_name, fi.klass, fi.description, fi.author);
+
+  for (gint i = 0; i < fi.n_properties; i++) {
+    b200vf_property_info p;
+    GParamSpec *ps = NULL;
+    GParamFlags fl = G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS;
+    b200vf_factory_property (fi.factory, i, &p);
+    if (p.controllable) fl |= GST_PARAM_CONTROLLABLE;
+    /* perspective's "matrix" is a GValueArray of 9 doubles in the reference (gstperspective.c:222-232); the
+     * nine matrix-N doubles are installed too so that either spelling works */
+    switch (p.type) {
+      case B200VF_PROP_UINT: ps = g_param_spec_uint (p.name, p.name, p.name, (guint) p.min, (guint) p.max, (guint) p.def, fl); break;
+      case B200VF_PROP_INT: ps = g_param_spec_int (p.name, p.name, p.name, (gint) p.min, (gint) p.max, (gint) p.def, fl); break;
+      case B200VF_PROP_BOOL: ps = g_param_spec_boolean (p.name, p.name, p.name, p.def != 0, fl); break;
+      case B200VF_PROP_DOUBLE: ps = g_param_spec_double (p.name, p.name, p.name, p.min, p.max, p.def, fl); break;
+      case B200VF_PROP_ENUM: ps = g_param_spec_enum (p.name, p.name, p.name, enum_type_for (fi.type_name, &p), (gint) p.def, fl); break;
+    }
+    g_object_class_install_property (oc, PROP_FIRST + i, ps);
+  }
+
+  if (is_bayer_plugin_factory (fi.factory)) {
+    GstCaps *raw = raw_caps_for (&fi);
+    GstCaps *bayer = gst_caps_from_string ("video/x-bayer,format=(string){bggr,grbg,gbrg,rggb},"
+        "width=(int)[1,MAX],height=(int)[1,MAX],framerate=(fraction)[0/1,MAX]");
+    gboolean to_rgb = !strcmp (fi.factory, "bayer2rgb");
+    gst_element_class_add_pad_template (ec, gst_pad_template_new ("src", GST_PAD_SRC, GST_PAD_ALWAYS, to_rgb ? raw : bayer));
+    gst_element_class_add_pad_template (ec, gst_pad_template_new ("sink", GST_PAD_SINK, GST_PAD_ALWAYS, to_rgb ? bayer : raw));
+    bc->transform_caps = GST_DEBUG_FUNCPTR (b200vf_bayer_transform_caps);
+    bc->get_unit_size = GST_DEBUG_FUNCPTR (b200vf_bayer_get_unit_size);
+    bc->set_caps = GST_DEBUG_FUNCPTR (b200vf_bayer_set_caps);
+    bc->transform = GST_DEBUG_FUNCPTR (b200vf_bayer_transform);
+    gst_caps_unref (raw);
+    gst_caps_unref (bayer);
+  } else {
+    GstVideoFilterClass *vc = GST_VIDEO_FILTER_CLASS (g_class);
+    GstCaps *raw = raw_caps_for (&fi);
+    gst_element_class_add_pad_template (ec, gst_pad_template_new ("src", GST_PAD_SRC, GST_PAD_ALWAYS, raw));
+    gst_element_class_add_pad_template (ec, gst_pad_template_new ("sink", GST_PAD_SINK, GST_PAD_ALWAYS, raw));
+    gst_caps_unref (raw);
+    vc->set_info = GST_DEBUG_FUNCPTR (b200vf_set_info);
+    if (fi.in_place) vc->transform_frame_ip = GST_DEBUG_FUNCPTR (b200vf_transform_frame_ip);
+    else vc->transform_frame = GST_DEBUG_FUNCPTR (b200vf_transform_frame);
+  }
+  bc->start = GST_DEBUG_FUNCPTR (b200vf_start);
+  bc->stop = GST_DEBUG_FUNCPTR (b200vf_stop);
+  bc->before_transform = GST_DEBUG_FUNCPTR (b200vf_before_transform);
+}
+
+static void
+b200vf_instance_init (GTypeInstance * instance, gpointer g_class)
+{
+  GstB200vf *self = B200VF (instance);
+  self->device = 0;
+  /* a device-less mirror holds the property values until start() binds the GPU */
+  b200vf_element_factory_make (NULL, ((GstB200vfClass *) g_class)->factory, &self->el);
+  if (is_bayer_plugin_factory (((GstB200vfClass *) g_class)->factory))
+    gst_base_transform_set_in_place (GST_BASE_TRANSFORM (instance), TRUE);     /* gstbayer2rgb.c:209 */
+}
+
+/* abstract intermediate types keep the reference's GType hierarchy (gstgeometrictransform.c:406-432) */
+static GType
+abstract_type (const gchar * name, GType parent)
+{
+  GType t = g_type_from_name (name);
+  if (!t) {
+    GTypeInfo info = { sizeof (GstB200vfClass), NULL, NULL, NULL, NULL, NULL, sizeof (GstB200vf), 0, NULL, NULL };
+    t = g_type_register_static (parent, name, &info, G_TYPE_FLAG_ABSTRACT);
+  }
+  return t;
+}
+
+static gboolean
+plugin_init (GstPlugin * plugin)
+{
+  GST_DEBUG_CATEGORY_INIT (b200vf_debug, "b200vf", 0, "B200 video filters");
+  gboolean ok = TRUE;
+  for (gint i = 0; i < b200vf_factory_count (); i++) {
+    b200vf_factory_info fi;
+    if (b200vf_factory_get (i, &fi) != B200VF_OK || strcmp (fi.plugin, STR (B200VF_PLUGIN))) continue;
+    GType parent = GST_TYPE_VIDEO_FILTER;
+    if (!strcmp (fi.parent_type_name, "GstBaseTransform")) parent = GST_TYPE_BASE_TRANSFORM;
+    else if (!strcmp (fi.parent_type_name, "GstGeometricTransform")) parent = abstract_type ("GstGeometricTransform", GST_TYPE_VIDEO_FILTER);
+    else if (!strcmp (fi.parent_type_name, "GstCircleGeometricTransform"))
+      parent = abstract_type ("GstCircleGeometricTransform", abstract_type ("GstGeometricTransform", GST_TYPE_VIDEO_FILTER));
+    GTypeInfo info = { sizeof (GstB200vfClass), NULL, NULL, b200vf_class_init, NULL, fi.factory, sizeof (GstB200vf), 0,
+      b200vf_instance_init, NULL };
+    GType t = g_type_register_static (parent, fi.type_name, &info, 0);
+    ok &= gst_element_register (plugin, fi.factory, GST_RANK_NONE, t);
+  }
+  return ok;
+}
+
+/* one level of indirection so that B200VF_PLUGIN is expanded before GST_PLUGIN_DEFINE pastes it */
+#define B200VF_DEFINE_PLUGIN(name) \
+  GST_PLUGIN_DEFINE (GST_VERSION_MAJOR, GST_VERSION_MINOR, name, "B200-native " STR (name) " (sm_100a kernels behind the stock element surface)", \
+      plugin_init, VERSION, "LGPL", PACKAGE, "https://gstreamer.freedesktop.org")
+B200VF_DEFINE_PLUGIN (B200VF_PLUGIN)

@@ -44,7 +44,15 @@ int find_bayer (const char *n) {
 }
 
 enum PType { P_UINT, P_INT, P_BOOL, P_DOUBLE, P_ENUM };
-struct PropDef { const char *name; PType type; double lo, hi, def; std::vector<const char *> nicks; };
+struct PropDef {
+  const char *name; PType type; double lo, hi, def; std::vector<const char *> nicks;
+  // GST_PARAM_CONTROLLABLE on everything except the enum presets/modes and perspective's matrix (API dump)
+  bool controllable () const { return !(type == P_ENUM && (!strcmp (name, "preset") || !strcmp (name, "mode"))) && strncmp (name, "matrix-", 7) != 0; }
+};
+
+struct ElementMeta { const char *factory, *plugin, *plugin_description, *plugin_license, *type_name, *parent_type_name,
+  *klass, *long_name, *description, *author; };
+#include "element_metadata.inc"
 
 const double kMaxD = 1.7976931348623157e308;
 const double kPi = 3.1415926535897932384626433832795028841971693993751;
@@ -459,4 +467,53 @@ B200VF_API int b200vf_element_transform_host (b200vf_element *e, const void *h_i
   }
   for (int k = 0; k < kHostStreams; k++) B200VF_CHECK_CUDA (cudaStreamSynchronize (e->hs[k]));
   return B200VF_OK;
+}
+
+// ------------------------------------------------------------ factory introspection
+static int fill_info (const FactoryDef &f, b200vf_factory_info *out) {
+  memset (out, 0, sizeof *out);
+  out->factory = f.name;
+  for (const auto &m : kElementMeta)
+    if (!strcmp (m.factory, f.name)) {
+      out->plugin = m.plugin; out->plugin_description = m.plugin_description; out->plugin_license = m.plugin_license;
+      out->type_name = m.type_name; out->parent_type_name = m.parent_type_name; out->klass = m.klass;
+      out->long_name = m.long_name; out->description = m.description; out->author = m.author;
+    }
+  B200VF_REQUIRE (out->plugin, B200VF_E_INVAL, "factory `%s` has no metadata row", f.name);
+  out->in_place = (f.kind == K_COLOREFFECTS || f.kind == K_CHROMAHOLD);
+  out->n_properties = (int) f.props.size ();
+  out->n_formats = (int) f.formats.size ();
+  return B200VF_OK;
+}
+B200VF_API int b200vf_factory_count (void) { return (int) factories ().size (); }
+B200VF_API int b200vf_factory_get (int index, b200vf_factory_info *out) {
+  B200VF_REQUIRE (out && index >= 0 && index < (int) factories ().size (), B200VF_E_INVAL, "factory_get: index %d", index);
+  return fill_info (factories ()[index], out);
+}
+B200VF_API int b200vf_factory_find (const char *factory, b200vf_factory_info *out) {
+  B200VF_REQUIRE (factory && out, B200VF_E_INVAL, "factory_find: NULL argument");
+  for (const auto &f : factories ()) if (!strcmp (f.name, factory)) return fill_info (f, out);
+  b200vf_set_error ("no such element factory `%s`", factory);
+  return B200VF_E_UNSUPPORTED;
+}
+B200VF_API int b200vf_factory_property (const char *factory, int index, b200vf_property_info *out) {
+  B200VF_REQUIRE (factory && out, B200VF_E_INVAL, "factory_property: NULL argument");
+  for (const auto &f : factories ()) {
+    if (strcmp (f.name, factory)) continue;
+    B200VF_REQUIRE (index >= 0 && index < (int) f.props.size (), B200VF_E_INVAL, "factory_property: index %d", index);
+    const PropDef &p = f.props[index];
+    out->name = p.name; out->type = (int) p.type; out->min = p.lo; out->max = p.hi; out->def = p.def;
+    out->controllable = p.controllable () ? 1 : 0;
+    out->n_nicks = (int) p.nicks.size ();
+    out->nicks = p.nicks.empty () ? nullptr : p.nicks.data ();
+    return B200VF_OK;
+  }
+  b200vf_set_error ("no such element factory `%s`", factory);
+  return B200VF_E_UNSUPPORTED;
+}
+B200VF_API const char *b200vf_factory_format (const char *factory, int index) {
+  if (!factory) return nullptr;
+  for (const auto &f : factories ())
+    if (!strcmp (f.name, factory)) return (index >= 0 && index < (int) f.formats.size ()) ? f.formats[index] : nullptr;
+  return nullptr;
 }

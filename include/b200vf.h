@@ -271,6 +271,41 @@ int b200vf_element_transform_host (b200vf_element *e, const void *h_in, void *h_
  * elements d_out may equal d_in. */
 int b200vf_element_transform_device (b200vf_element *e, const void *d_in, void *d_out, int nframes, void *stream);
 
+/* ------------------------------------------------- factory introspection
+ * What gst-inspect prints for each element, so that the C/GLib shells (gst/gstb200vf.c) can register the
+ * factories, install the GObject properties and build the pad templates from one table instead of
+ * repeating it (GST_ELEMENT_REGISTER + class_init of each reference element, e.g. gst/gaudieffects/gstburn.c:
+ * 120-160; golden dump docs/plugins/gst_plugins_cache.json). */
+typedef struct b200vf_factory_info {
+  const char *factory;            /* "burn" */
+  const char *plugin;             /* "gaudieffects" */
+  const char *plugin_description;
+  const char *plugin_license;
+  const char *type_name;          /* "GstBurn" */
+  const char *parent_type_name;   /* "GstVideoFilter", "GstBaseTransform", "GstGeometricTransform", "GstCircleGeometricTransform" */
+  const char *klass;              /* "Filter/Effect/Video" */
+  const char *long_name;
+  const char *description;
+  const char *author;
+  int in_place;                   /* 1: transform_frame_ip (coloreffects, chromahold) */
+  int n_properties;
+  int n_formats;                  /* raw video formats of the pad template (sink == src except the bayer elements) */
+} b200vf_factory_info;
+typedef enum b200vf_prop_type { B200VF_PROP_UINT = 0, B200VF_PROP_INT, B200VF_PROP_BOOL, B200VF_PROP_DOUBLE, B200VF_PROP_ENUM } b200vf_prop_type;
+typedef struct b200vf_property_info {
+  const char *name;
+  int type;                       /* b200vf_prop_type */
+  double min, max, def;
+  int controllable;               /* GST_PARAM_CONTROLLABLE */
+  int n_nicks;                    /* enum nicks, value i = nicks[i] */
+  const char *const *nicks;
+} b200vf_property_info;
+int b200vf_factory_count (void);
+int b200vf_factory_get (int index, b200vf_factory_info *out);
+int b200vf_factory_find (const char *factory, b200vf_factory_info *out);
+int b200vf_factory_property (const char *factory, int index, b200vf_property_info *out);
+const char *b200vf_factory_format (const char *factory, int index);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,7 +109,9 @@ def main():
                 props[pn] = {k: pd.get(k) for k in ("type", "min", "max", "default", "controllable") if k in pd}
             pads = {pn: pd.get("caps") for pn, pd in el.get("pad-templates", {}).items()}
             surf[name] = {"plugin": plugin, "klass": el.get("klass"), "hierarchy": el.get("hierarchy"), "properties": props,
-                          "pad-templates": pads}
+                          "pad-templates": pads, "long-name": el.get("long-name"), "description": el.get("description"),
+                          "author": el.get("author"), "rank": el.get("rank"),
+                          "plugin-description": cache[plugin].get("description"), "plugin-license": cache[plugin].get("license")}
     json.dump(surf, open(os.path.join(HERE, "element_surface.json"), "w"), indent=1, sort_keys=True)
     print("wrote %d arrays, %d elements" % (len(g), len(surf)))
 

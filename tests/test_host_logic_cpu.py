@@ -233,3 +233,31 @@ def test_element_without_device_cannot_transform(vf):
     with pytest.raises(vf.B200vfError) as err:
         e.transform(np.zeros(8 * 8 * 4, np.uint8))
     assert err.value.status == vf.E_NO_DEVICE
+
+
+def test_factory_introspection_matches_reference_api_dump(vf):
+    """what the GLib shells register (gst/gstb200vf.c reads exactly this table): plugin, GType name and parent,
+    klass, long name, description, author, controllable flags == the reference's docs/plugins/gst_plugins_cache.json"""
+    surf = json.load(open(os.path.join(ROOT, "tests", "golden", "element_surface.json")))
+    fac = vf.factories()
+    assert set(fac) == set(surf) - {"diffuse"}
+    for name, f in fac.items():
+        e = surf[name]
+        assert f["plugin"] == e["plugin"] and f["type_name"] == e["hierarchy"][0] and f["parent_type_name"] == e["hierarchy"][1]
+        assert f["klass"] == e["klass"] and f["long_name"] == e["long-name"] and f["description"] == e["description"]
+        assert f["author"] == e["author"] and f["plugin_license"] == e["plugin-license"]
+        assert f["in_place"] == (1 if name in ("coloreffects", "chromahold") else 0)
+        props = {p["name"]: p for p in f["properties"]}
+        for pn, pd in e["properties"].items():
+            if pd["type"] == "GValueArray":
+                assert all(not props["matrix-%d" % i]["controllable"] for i in range(9))
+                continue
+            assert props[pn]["controllable"] == bool(pd.get("controllable")), (name, pn)
+            kind = {"guint": 0, "gint": 1, "gboolean": 2, "gdouble": 3}.get(pd["type"], 4)
+            assert props[pn]["type"] == kind, (name, pn, pd["type"])
+        caps = e["pad-templates"]["src" if name == "rgb2bayer" else "sink"] if name not in ("bayer2rgb",) else e["pad-templates"]["src"]
+        if name == "rgb2bayer":
+            caps = e["pad-templates"]["sink"]
+        fm = re.findall(r"format: \{ ([^}]*) \}", caps)
+        want = [x.strip() for x in fm[0].split(",")] if fm else re.findall(r"format: (\w+)", caps)
+        assert sorted(f["formats"]) == sorted(want), (name, f["formats"], want)
