@@ -60,6 +60,7 @@ _SIGS = {
     "b200vf_memcpy_d2h": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "b200vf_bayer2rgb": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200vf_bayer2rgb_shard": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200vf_bayer2rgb_shard_fused": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b200vf_rgb2bayer": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _vp]),
     "b200vf_lut4": (_i, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "b200vf_lut_burn": (_i, [_i, _vp]),
@@ -85,6 +86,7 @@ _SIGS = {
     "b200vf_shard_rows": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "b200vf_comm_halo_exchange": (_i, [_vp, _vp, _sz, _i, _i, _sz, _i, _vp]),
     "b200vf_comm_barrier": (_i, [_vp, _vp]),
+    "b200vf_comm_allgather_rows": (_i, [_vp, _vp, _sz, _i, _sz, _i, _vp]),
     "b200vf_factory_count": (_i, []),
     "b200vf_factory_get": (_i, [_i, _vp]),
     "b200vf_factory_find": (_i, [C.c_char_p, _vp]),
@@ -225,6 +227,15 @@ class Context:
                                          height, nframes, pattern, offs[0], offs[1], offs[2],
                                          None if lt is None else _hptr(lt), None if la is None else _hptr(la), stream))
 
+    def bayer2rgb_shard_fused(self, src, src_stride, dst, dst_stride, width, full_height, row0, rows, pattern, offs,
+                              luma_table=None, lut=None, nframes=1, src_frame_stride=0, dst_frame_stride=0, stream=None):
+        lt = None if luma_table is None else np.ascontiguousarray(luma_table, np.uint8)
+        la = _lut_arg(lut)
+        check(lib.b200vf_bayer2rgb_shard_fused(self.h, _ptr(src), src_stride, src_frame_stride, _ptr(dst), dst_stride,
+                                               dst_frame_stride, width, full_height, row0, rows, nframes, pattern,
+                                               offs[0], offs[1], offs[2], None if lt is None else _hptr(lt),
+                                               None if la is None else _hptr(la), stream))
+
     def rgb2bayer(self, src, src_stride, dst, dst_stride, width, height, pattern, nframes=1, stream=None):
         check(lib.b200vf_rgb2bayer(self.h, _ptr(src), src_stride, src_stride * height, _ptr(dst), dst_stride,
                                    dst_stride * height, width, height, nframes, pattern, stream))
@@ -357,6 +368,31 @@ def gt_resolve_map(map_xy, width, height, off_edge):
     m = np.ascontiguousarray(map_xy, np.float64)
     check(lib.b200vf_gt_resolve_map(_hptr(m), width, height, off_edge, _hptr(idx)))
     return idx
+
+
+class Comm:
+    """NCCL communicator of the row-shard path (one process per GPU). `bcast(tensor_or_bytes)` is how the caller
+    distributes rank 0's 128-byte unique id (torch.distributed, MPI, a file ...)."""
+
+    def __init__(self, ctx, rank, nranks, bcast):
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            check(lib.b200vf_comm_unique_id(buf))
+        idb = (C.c_uint8 * 128)(*bcast(bytes(buf)))
+        h = _vp()
+        check(lib.b200vf_comm_create(ctx.h, idb, rank, nranks, C.byref(h)))
+        self.h, self.rank, self.nranks = h, rank, nranks
+
+    def halo_exchange(self, buf, row_bytes, rows, halo, frame_stride, nframes=1, stream=None):
+        check(lib.b200vf_comm_halo_exchange(self.h, _ptr(buf), row_bytes, rows, halo, frame_stride, nframes, stream))
+
+    def allgather_rows(self, full, row_bytes, full_rows, frame_stride=0, nframes=1, stream=None):
+        check(lib.b200vf_comm_allgather_rows(self.h, _ptr(full), row_bytes, full_rows, frame_stride, nframes, stream))
+
+    def close(self):
+        if self.h:
+            lib.b200vf_comm_destroy(self.h)
+            self.h = None
 
 
 def shard_rows(height, rank, nranks):

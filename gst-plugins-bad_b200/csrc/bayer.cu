@@ -251,6 +251,19 @@ B200VF_API int b200vf_bayer2rgb_shard (b200vf_ctx *ctx, const uint8_t *d_src, in
       width, full_height, row0, rows, nframes, pattern, r_off, g_off, b_off, true, nullptr, nullptr, stream);
 }
 
+B200VF_API int b200vf_bayer2rgb_shard_fused (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
+    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int full_height, int row0, int rows,
+    int nframes, int pattern, int r_off, int g_off, int b_off, const uint8_t *luma_table768,
+    const uint8_t lut[4][256], void *stream)
+{
+  if (row0 + rows == full_height && row0 > 0)
+    B200VF_REQUIRE (rows >= 4, B200VF_E_INVAL, "bayer2rgb_shard: the last shard needs >= 4 rows (has %d)", rows);
+  if (row0 == 0 && rows < full_height)
+    B200VF_REQUIRE (rows >= 2, B200VF_E_INVAL, "bayer2rgb_shard: the first shard needs >= 2 rows (has %d)", rows);
+  return bayer_common (ctx, d_src, src_stride, src_frame_stride, d_dst, dst_stride, dst_frame_stride,
+      width, full_height, row0, rows, nframes, pattern, r_off, g_off, b_off, true, luma_table768, lut, stream);
+}
+
 // ------------------------------------------------------------------ rgb2bayer
 // gst/bayer/gstrgb2bayer.c:254-267: dest[i] = byte 3 / 1 / 2 of the ARGB pixel
 // depending on (row, column) parity vs the pattern. 4 pixels per lane.

@@ -169,6 +169,31 @@ B200VF_API int b200vf_comm_halo_exchange (b200vf_comm *comm, uint8_t *d_buf, siz
   return B200VF_OK;
 }
 
+B200VF_API int b200vf_comm_allgather_rows (b200vf_comm *comm, uint8_t *d_full, size_t row_bytes, int full_rows,
+    size_t frame_stride, int nframes, void *stream)
+{
+  B200VF_REQUIRE (comm && d_full && row_bytes > 0 && full_rows > 0 && nframes > 0, B200VF_E_INVAL, "allgather_rows: bad argument");
+  if (comm->nranks == 1) return B200VF_OK;
+  cudaStream_t s = b200vf_stream (comm->ctx, stream);
+  int my0 = 0, myn = 0;
+  int rc = b200vf_shard_rows (full_rows, comm->rank, comm->nranks, &my0, &myn);
+  if (rc) return rc;
+  for (int f = 0; f < nframes; f++) {
+    uint8_t *base = d_full + (size_t) f * frame_stride;
+    NCCL_CHECK (nccl ().GroupStart ());
+    for (int r = 0; r < comm->nranks; r++) {
+      if (r == comm->rank) continue;
+      int r0 = 0, rn = 0;
+      rc = b200vf_shard_rows (full_rows, r, comm->nranks, &r0, &rn);
+      if (rc) { nccl ().GroupEnd (); return rc; }
+      NCCL_CHECK (nccl ().Send (base + (size_t) my0 * row_bytes, (size_t) myn * row_bytes, ncclUint8, r, comm->comm, s));
+      NCCL_CHECK (nccl ().Recv (base + (size_t) r0 * row_bytes, (size_t) rn * row_bytes, ncclUint8, r, comm->comm, s));
+    }
+    NCCL_CHECK (nccl ().GroupEnd ());
+  }
+  return B200VF_OK;
+}
+
 B200VF_API int b200vf_comm_barrier (b200vf_comm *comm, void *stream) {
   B200VF_REQUIRE (comm, B200VF_E_INVAL, "comm_barrier: NULL argument");
   cudaStream_t s = b200vf_stream (comm->ctx, stream);

@@ -124,6 +124,12 @@ int b200vf_bayer2rgb_shard (b200vf_ctx *ctx, const uint8_t *d_src, int src_strid
     uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int full_height, int row0, int rows,
     int nframes, int pattern, int r_off, int g_off, int b_off, void *stream);
 
+/* b200vf_bayer2rgb_shard with the fused epilogue of b200vf_bayer2rgb_fused (BASELINE.json config 5 on N GPUs). */
+int b200vf_bayer2rgb_shard_fused (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
+    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int full_height, int row0, int rows,
+    int nframes, int pattern, int r_off, int g_off, int b_off, const uint8_t *luma_table768,
+    const uint8_t lut[4][256], void *stream);
+
 /* Replaces the per-pixel select loop of gst_rgb2bayer_transform
  * (gst/bayer/gstrgb2bayer.c:254-267); src is ARGB (4 B/px). */
 int b200vf_rgb2bayer (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
@@ -240,6 +246,11 @@ int b200vf_shard_rows (int height, int rank, int nranks, int *row0, int *rows);
 int b200vf_comm_halo_exchange (b200vf_comm *comm, uint8_t *d_buf, size_t row_bytes, int rows, int halo,
     size_t frame_stride, int nframes, void *stream);
 int b200vf_comm_barrier (b200vf_comm *comm, void *stream);
+/* All-gather of row shards (geometrictransform: the gather may read any source row): every rank
+ * holds a full-size frame buffer with its own rows [row0,row0+rows) (b200vf_shard_rows) filled in; afterwards
+ * all `full_rows` rows are valid on every rank. One grouped ncclSend/ncclRecv set per frame. */
+int b200vf_comm_allgather_rows (b200vf_comm *comm, uint8_t *d_full, size_t row_bytes, int full_rows,
+    size_t frame_stride, int nframes, void *stream);
 
 /* ----------------------------------------------------- element mirror (host)
  * A GLib-free mirror of the reference's element surface so pipelines can be
