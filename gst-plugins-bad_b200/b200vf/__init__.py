@@ -87,6 +87,8 @@ _SIGS = {
     "b200vf_comm_halo_exchange": (_i, [_vp, _vp, _sz, _i, _i, _sz, _i, _vp]),
     "b200vf_comm_barrier": (_i, [_vp, _vp]),
     "b200vf_comm_allgather_rows": (_i, [_vp, _vp, _sz, _i, _sz, _i, _vp]),
+    "b200vf_comm_exchange_rows": (_i, [_vp, _vp, _sz, _i, _vp, _vp, _sz, _i, _vp]),
+    "b200vf_gt_index_row_range": (_i, [_vp, _sz, _i, C.POINTER(_i), C.POINTER(_i)]),
     "b200vf_factory_count": (_i, []),
     "b200vf_factory_get": (_i, [_i, _vp]),
     "b200vf_factory_find": (_i, [C.c_char_p, _vp]),
@@ -389,10 +391,23 @@ class Comm:
     def allgather_rows(self, full, row_bytes, full_rows, frame_stride=0, nframes=1, stream=None):
         check(lib.b200vf_comm_allgather_rows(self.h, _ptr(full), row_bytes, full_rows, frame_stride, nframes, stream))
 
+    def exchange_rows(self, full, row_bytes, full_rows, need_lo, need_hi, frame_stride=0, nframes=1, stream=None):
+        lo = np.ascontiguousarray(need_lo, np.int32)
+        hi = np.ascontiguousarray(need_hi, np.int32)
+        check(lib.b200vf_comm_exchange_rows(self.h, _ptr(full), row_bytes, full_rows, _hptr(lo), _hptr(hi), frame_stride,
+                                            nframes, stream))
+
     def close(self):
         if self.h:
             lib.b200vf_comm_destroy(self.h)
             self.h = None
+
+
+def gt_index_row_range(index, width):
+    a = np.ascontiguousarray(index, np.int32)
+    lo, hi = _i(0), _i(0)
+    check(lib.b200vf_gt_index_row_range(_hptr(a), a.size, width, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
 
 
 def shard_rows(height, rank, nranks):

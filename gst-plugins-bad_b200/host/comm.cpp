@@ -194,6 +194,35 @@ B200VF_API int b200vf_comm_allgather_rows (b200vf_comm *comm, uint8_t *d_full, s
   return B200VF_OK;
 }
 
+B200VF_API int b200vf_comm_exchange_rows (b200vf_comm *comm, uint8_t *d_full, size_t row_bytes, int full_rows,
+    const int *need_lo, const int *need_hi, size_t frame_stride, int nframes, void *stream)
+{
+  B200VF_REQUIRE (comm && d_full && need_lo && need_hi && row_bytes > 0 && full_rows > 0 && nframes > 0, B200VF_E_INVAL,
+      "exchange_rows: bad argument");
+  if (comm->nranks == 1) return B200VF_OK;
+  cudaStream_t s = b200vf_stream (comm->ctx, stream);
+  int my0 = 0, myn = 0;
+  int rc = b200vf_shard_rows (full_rows, comm->rank, comm->nranks, &my0, &myn);
+  if (rc) return rc;
+  auto clip = [] (int a0, int a1, int b0, int b1, int &o0, int &o1) { o0 = a0 > b0 ? a0 : b0; o1 = a1 < b1 ? a1 : b1; return o1 > o0; };
+  for (int f = 0; f < nframes; f++) {
+    uint8_t *base = d_full + (size_t) f * frame_stride;
+    NCCL_CHECK (nccl ().GroupStart ());
+    for (int r = 0; r < comm->nranks; r++) {
+      if (r == comm->rank) continue;
+      int r0 = 0, rn = 0, a, b;
+      rc = b200vf_shard_rows (full_rows, r, comm->nranks, &r0, &rn);
+      if (rc) { nccl ().GroupEnd (); return rc; }
+      if (clip (my0, my0 + myn, need_lo[r], need_hi[r], a, b))           // my rows that peer r reads
+        NCCL_CHECK (nccl ().Send (base + (size_t) a * row_bytes, (size_t) (b - a) * row_bytes, ncclUint8, r, comm->comm, s));
+      if (clip (r0, r0 + rn, need_lo[comm->rank], need_hi[comm->rank], a, b))   // peer r's rows that I read
+        NCCL_CHECK (nccl ().Recv (base + (size_t) a * row_bytes, (size_t) (b - a) * row_bytes, ncclUint8, r, comm->comm, s));
+    }
+    NCCL_CHECK (nccl ().GroupEnd ());
+  }
+  return B200VF_OK;
+}
+
 B200VF_API int b200vf_comm_barrier (b200vf_comm *comm, void *stream) {
   B200VF_REQUIRE (comm, B200VF_E_INVAL, "comm_barrier: NULL argument");
   cudaStream_t s = b200vf_stream (comm->ctx, stream);

@@ -395,3 +395,18 @@ B200VF_API int b200vf_gt_resolve_map (const double *map_xy, int width, int heigh
   }
   return B200VF_OK;
 }
+
+B200VF_API int b200vf_gt_index_row_range (const int32_t *index, size_t n, int width, int *row_lo, int *row_hi) {
+  B200VF_REQUIRE (index && row_lo && row_hi && width > 0, B200VF_E_INVAL, "gt_index_row_range: bad argument");
+  int32_t lo = INT32_MAX, hi = -1;
+  for (size_t i = 0; i < n; i++) {
+    int32_t v = index[i];
+    if (v < 0) continue;
+    if (v < lo) lo = v;
+    if (v > hi) hi = v;
+  }
+  if (hi < 0) { *row_lo = *row_hi = 0; return B200VF_OK; }
+  *row_lo = lo / width;
+  *row_hi = hi / width + 1;
+  return B200VF_OK;
+}

@@ -251,6 +251,14 @@ int b200vf_comm_barrier (b200vf_comm *comm, void *stream);
  * all `full_rows` rows are valid on every rank. One grouped ncclSend/ncclRecv set per frame. */
 int b200vf_comm_allgather_rows (b200vf_comm *comm, uint8_t *d_full, size_t row_bytes, int full_rows,
     size_t frame_stride, int nframes, void *stream);
+/* Banded variant: smooth maps (fisheye, bulge, ...) read a bounded band of source rows per output shard.
+ * need_lo/need_hi[r] = the source rows [lo,hi) rank r's output shard reads (b200vf_gt_index_row_range over its
+ * part of the index table; every rank builds the same table, so every rank knows everybody's band). Each rank
+ * sends the part of its own rows a peer needs and receives the part of its band it does not own. */
+int b200vf_comm_exchange_rows (b200vf_comm *comm, uint8_t *d_full, size_t row_bytes, int full_rows,
+    const int *need_lo, const int *need_hi, size_t frame_stride, int nframes, void *stream);
+/* min / max+1 source row referenced by index[0..n) (entries < 0 ignored); lo = hi = 0 when none. */
+int b200vf_gt_index_row_range (const int32_t *index, size_t n, int width, int *row_lo, int *row_hi);
 
 /* ----------------------------------------------------- element mirror (host)
  * A GLib-free mirror of the reference's element surface so pipelines can be

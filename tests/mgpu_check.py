@@ -133,9 +133,13 @@ def main():
     frame = rng.integers(0, 256, (h, rb), dtype=np.uint8)
     full[r0:r0 + rows] = torch.from_numpy(frame[r0:r0 + rows]).cuda()
     torch.cuda.synchronize()
-    b200vf.check(b200vf.lib.b200vf_comm_allgather_rows(comm, full.data_ptr(), rb, h, 0, 1, st))
     m = b200vf.gt_build_map("fisheye", w, h)
     idx = b200vf.gt_resolve_map(m, w, h, 1)
+    # banded exchange: only the source rows each output shard reads travel (all-gather is the fallback)
+    bands = [b200vf.gt_index_row_range(idx[a:a + b], w) for (a, b) in [b200vf.shard_rows(h, r, world) for r in range(world)]]
+    lo = np.array([b[0] for b in bands], np.int32); hi = np.array([b[1] for b in bands], np.int32)
+    b200vf.check(b200vf.lib.b200vf_comm_exchange_rows(comm, full.data_ptr(), rb, h, lo.ctypes.data_as(ctypes.c_void_p),
+                                                      hi.ctypes.data_as(ctypes.c_void_p), 0, 1, st))
     d_idx = torch.from_numpy(np.ascontiguousarray(idx[r0:r0 + rows])).cuda()
     dst = torch.zeros((1, rows, rb), dtype=torch.uint8, device="cuda")
     ctx.remap(full, dst, d_idx, w, rows, 4, rb, stream=st)           # a shard of output rows: `height` = rows of this shard

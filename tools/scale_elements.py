@@ -74,10 +74,13 @@ def main():
     dst = torch.empty((n, rows, rb), dtype=torch.uint8, device="cuda")
     idx = b200vf.gt_resolve_map(b200vf.gt_build_map("fisheye", w, h), w, h, 1)
     d_idx = torch.from_numpy(np.ascontiguousarray(idx[r0:r0 + rows])).cuda()
+    bands = [b200vf.gt_index_row_range(idx[a:a + b], w) for (a, b) in [b200vf.shard_rows(h, r, world) for r in range(world)]]
+    need_lo, need_hi = [b[0] for b in bands], [b[1] for b in bands]
+    out["fisheye_bands"] = bands
 
     def fstep():
         if comm:
-            comm.allgather_rows(full, rb, h, h * rb, n, st)
+            comm.exchange_rows(full, rb, h, need_lo, need_hi, h * rb, n, st)
         for i in range(n):          # frames have different src/dst pitches here: one launch per frame
             ctx.remap(full[i], dst[i], d_idx, w, rows, 4, rb, stream=st)
     t = timed(fstep, 3)
