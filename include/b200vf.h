@@ -177,6 +177,12 @@ int b200vf_gauss_kernel (float sigma, float *kernel, float *kernel_sum, int capa
 int b200vf_gaussblur (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, int width, int full_height,
     int row0, int rows, int stride, size_t frame_stride, int nframes, int p0,
     const float *kernel, const float *kernel_sum, int windowsize, int exact, void *stream);
+/* Test hook: the blur divides by per-column/row constants through their
+ * reciprocal plus two FMA corrections; this counts the fp32 values a (bit
+ * patterns [lo_bits, hi_bits)) for which that differs from IEEE a / divisor
+ * (must be 0 over the range the host enables it for, see gaussblur.cu div_rn). */
+int b200vf_gauss_selftest_div (b200vf_ctx *ctx, float divisor, uint32_t lo_bits, uint32_t hi_bits,
+    unsigned long long *mismatches);
 
 /* ------------------------------------------------------- coloreffects plugin
  * In place (transform_frame_ip, gstcoloreffects.c:479-501).

@@ -100,3 +100,25 @@ def test_4k_sigma5_band_exact(ctx, vf, orc, rng):
     const = np.full((h, 4 * w), 93, np.uint8)
     out = run(ctx, vf, const, w, h, 5, 0)                # p0 = 0: no channel reaches into the zero slack (D5)
     assert (out == 93).all()
+
+
+def test_reciprocal_division_is_ieee_exact(ctx, vf):
+    """The blur divides by per-column/row constants with RN(1/b) and two FMA corrections when every tap is
+    >= 0 and of ordinary size (gaussblur.cu div_rn). Under that condition a dividend is 0 or in
+    [2^-64, 2^13): check EVERY fp32 of that range, for every divisor a frame edge can produce."""
+    lo, hi = (127 - 64) << 23, (127 + 13) << 23
+    assert ctx.gauss_selftest_div(1.0, 0, 1) == 0                      # a == +0
+    ndiv = 0
+    for sigma in [0.5, 1.2, 2.0, 5.0, 12.5, 20.0]:
+        k, ks = vf.gauss_kernel(sigma)
+        ws, c = len(k), len(k) // 2
+        divisors = set()
+        for i in range(c + 1):
+            divisors.add(np.float32(np.float64(ks[ws - 1]) - (np.float64(ks[i - 1]) if i else 0.0)))
+            divisors.add(np.float32(ks[c + i]))
+        for b in sorted(divisors):
+            assert ctx.gauss_selftest_div(b, lo, hi) == 0, (sigma, float(b))
+            ndiv += 1
+    assert ndiv > 100
+    # the self-test does detect a differing quotient: 2^60 / 2^-100 overflows, where the reciprocal route gives NaN
+    assert ctx.gauss_selftest_div(np.float32(2.0 ** -100), 187 << 23, (187 << 23) + 16) == 16
