@@ -80,6 +80,10 @@ _SIGS = {
     "b200vf_gt_build_map": (_i, [C.c_char_p, _i, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_double), _i, _vp]),
     "b200vf_gt_resolve_map": (_i, [_vp, _i, _i, _i, _vp]),
     "b200vf_remap": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _sz, _i, _u32, _vp]),
+    "b200vf_gt_packed_bound": (_sz, [_i, _i]),
+    "b200vf_gt_pack_index": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz)]),
+    "b200vf_gt_unpack_index": (_i, [_vp, _sz, _i, _i, _vp]),
+    "b200vf_remap_packed": (_i, [_vp, _vp, _vp, _vp, _i, _i, _sz, _i, _u32, _vp]),
     "b200vf_bayer2rgb_fused": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b200vf_comm_unique_id": (_i, [_vp]),
     "b200vf_comm_create": (_i, [_vp, _vp, _i, _i, C.POINTER(_vp)]),
@@ -289,6 +293,10 @@ class Context:
         check(lib.b200vf_remap(self.h, _ptr(src), _ptr(dst), _ptr(index), width, height, pixel_stride, row_stride,
                                row_stride * height, nframes, fill, stream))
 
+    def remap_packed(self, src, dst, packed, width, height, fill=0, nframes=1, stream=None):
+        check(lib.b200vf_remap_packed(self.h, _ptr(src), _ptr(dst), _ptr(packed), width, height, 4 * width * height,
+                                      nframes, fill, stream))
+
     def element(self, factory):
         return Element(self, factory)
 
@@ -376,6 +384,22 @@ def gt_resolve_map(map_xy, width, height, off_edge):
     idx = np.zeros((height, width), np.int32)
     m = np.ascontiguousarray(map_xy, np.float64)
     check(lib.b200vf_gt_resolve_map(_hptr(m), width, height, off_edge, _hptr(idx)))
+    return idx
+
+
+def gt_pack_index(index, width, height):
+    """-> (packed bytes as np.uint8 array, number of raw (uncoded) 128-pixel groups)"""
+    a = np.ascontiguousarray(index, np.int32)
+    buf = np.zeros(lib.b200vf_gt_packed_bound(width, height), np.uint8)
+    used, raw = _sz(0), _sz(0)
+    check(lib.b200vf_gt_pack_index(_hptr(a), width, height, _hptr(buf), buf.size, C.byref(used), C.byref(raw)))
+    return buf[:used.value].copy(), raw.value
+
+
+def gt_unpack_index(packed, width, height):
+    p = np.ascontiguousarray(packed, np.uint8)
+    idx = np.zeros((height, width), np.int32)
+    check(lib.b200vf_gt_unpack_index(_hptr(p), p.size, width, height, _hptr(idx)))
     return idx
 
 

@@ -22,6 +22,7 @@ struct b200vf_ctx {
   void *tma_encode = nullptr;      // cuTensorMapEncodeTiled entry point (driver API via cudart)
   unsigned int *tile_counters = nullptr;   // ring of work counters for dynamically scheduled kernels
   unsigned int tile_counter_next = 0;
+  cudaMemPool_t scratch_pool = nullptr;    // stream-ordered scratch (gaussblur pre-pass ...): never trimmed at synchronisation points
 };
 
 void b200vf_set_error (const char *fmt, ...);

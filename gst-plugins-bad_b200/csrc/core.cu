@@ -64,6 +64,29 @@ B200VF_API int b200vf_ctx_create (int device, b200vf_ctx **out) {
     delete c;
     return B200VF_E_CUDA;
   }
+  // scratch buffers come from a private stream-ordered pool that keeps its memory: the device's default pool
+  // gives everything back to the driver at each synchronisation (release threshold 0), which would re-map a
+  // frame-sized scratch on every frame of a pipeline that synchronises per buffer
+  {
+    cudaMemPoolProps props;
+    memset (&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    e = cudaMemPoolCreate (&c->scratch_pool, &props);
+    if (e == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      e = cudaMemPoolSetAttribute (c->scratch_pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    if (e != cudaSuccess) {
+      b200vf_set_error ("cudaMemPoolCreate: %s", cudaGetErrorString (e));
+      if (c->scratch_pool) cudaMemPoolDestroy (c->scratch_pool);
+      cudaStreamDestroy (c->stream);
+      delete c;
+      return B200VF_E_CUDA;
+    }
+  }
   *out = c;
   return B200VF_OK;
 }
@@ -73,6 +96,7 @@ B200VF_API void b200vf_ctx_destroy (b200vf_ctx *ctx) {
   cudaSetDevice (ctx->device);
   if (ctx->stream) cudaStreamDestroy (ctx->stream);
   if (ctx->tile_counters) cudaFree (ctx->tile_counters);
+  if (ctx->scratch_pool) cudaMemPoolDestroy (ctx->scratch_pool);
   delete ctx;
 }
 B200VF_API int b200vf_ctx_device (const b200vf_ctx *ctx) { return ctx ? ctx->device : -1; }

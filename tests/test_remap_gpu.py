@@ -60,3 +60,51 @@ def test_fisheye_4k_index_and_frame(ctx, vf, orc, rng):
     fr = frames.random_u8(rng, h, 4 * w)
     got = gpu_remap(ctx, vf, fr, idx, w, h, 4)
     assert np.array_equal(got, orc.remap(fr, m, w, h, 4, "clamp", False))
+
+
+def gpu_remap_packed(ctx, vf, fr, index, w, h, fill=0, nframes=1):
+    packed, raw = vf.gt_pack_index(index, w, h)
+    d_src = ctx.upload(fr)
+    d_dst = ctx.alloc(fr.size)
+    d_p = ctx.upload(packed)
+    ctx.remap_packed(d_src, d_dst, d_p, w, h, fill=fill, nframes=nframes)
+    assert ctx.last_kernel() == "remap4_packed"
+    return ctx.download(d_dst, fr.size).reshape(fr.shape), raw
+
+
+@pytest.mark.parametrize("w,h", [(300, 40), (128, 16), (100, 9), (257, 5)])
+def test_packed_table_all_maps(ctx, vf, orc, rng, w, h):
+    """the step-coded table drives the same gather: every map, every off-edge policy, ragged widths, AYUV fill"""
+    import refprops
+    fr = frames.random_u8(rng, h, 4 * w)
+    for el, plist in refprops.CASES.items():
+        if el == "diffuse":
+            continue
+        m = vf.gt_build_map(el, w, h, plist[0])
+        for name, off in OFF.items():
+            idx = vf.gt_resolve_map(m, w, h, off)
+            got, raw = gpu_remap_packed(ctx, vf, fr, idx, w, h, fill=0x808010ff)
+            want = orc.remap(fr, m, w, h, 4, name, True)
+            assert np.array_equal(got, want), (el, name, raw, np.argwhere(got != want)[:4])
+
+
+def test_packed_table_batch_and_raw_groups(ctx, vf, rng):
+    w, h, n = 384, 24, 3
+    idx = rng.integers(-1, w * h, (h, w), dtype=np.int32)                  # nothing codable: all groups raw
+    smooth = vf.gt_resolve_map(vf.gt_build_map("twirl", w, h), w, h, 1)
+    idx[::2] = smooth[::2]                                                 # every other row coded
+    fr = rng.integers(0, 256, (n * h, 4 * w), dtype=np.uint8)
+    got, raw = gpu_remap_packed(ctx, vf, fr, idx, w, h, fill=0x01020304, nframes=n)
+    assert 0 < raw < 3 * h
+    px = fr.reshape(n, h * w, 4)
+    want = np.where((idx.reshape(-1) >= 0)[None, :, None], px[:, np.maximum(idx.reshape(-1), 0)], np.array([4, 3, 2, 1], np.uint8))
+    assert np.array_equal(got.reshape(n, h * w, 4), want)
+
+
+def test_packed_fisheye_4k_equals_plain(ctx, vf, rng):
+    w, h = 3840, 2160
+    idx = vf.gt_resolve_map(vf.gt_build_map("fisheye", w, h), w, h, 1)
+    fr = frames.random_u8(rng, h, 4 * w)
+    got, raw = gpu_remap_packed(ctx, vf, fr, idx, w, h)
+    assert raw == 0
+    assert np.array_equal(got, gpu_remap(ctx, vf, fr, idx, w, h, 4))
