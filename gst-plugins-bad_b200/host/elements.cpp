@@ -153,8 +153,6 @@ struct b200vf_element {
   bool need_remap = true;
   int32_t *d_index = nullptr;
   size_t index_px = 0;
-  void *d_packed = nullptr;        // step-coded table (b200vf_gt_pack_index) when the map is smooth enough; else NULL
-  size_t packed_cap = 0;
   // host path: per-stream staging in HBM
   cudaStream_t hs[kHostStreams] = { nullptr, nullptr, nullptr };
   uint8_t *d_in[kHostStreams] = { nullptr, nullptr, nullptr };
@@ -220,24 +218,6 @@ int build_index (b200vf_element *e, cudaStream_t s) {
   // the table is built rarely; a synchronous copy keeps its lifetime trivial
   B200VF_CHECK_CUDA (cudaMemcpyAsync (e->d_index, idx.data (), npx * 4, cudaMemcpyHostToDevice, s));
   B200VF_CHECK_CUDA (cudaStreamSynchronize (s));
-  // 4-byte pixels, contiguous rows: the step-coded table (1.06 B/px) replaces the int32 one when at least
-  // half of the 128-pixel groups can be coded (smooth maps: all of them; kaleidoscope/ignored borders: most)
-  if (e->d_packed) { b200vf_free (e->ctx, e->d_packed); e->d_packed = nullptr; e->packed_cap = 0; }
-  if (e->fmt->pstride == 4 && e->in_stride == 4 * e->width && e->width <= 32767 && e->height <= 32767 &&
-      e->in_bytes % 16 == 0 && !getenv ("B200VF_REMAP_NO_PACK")) {
-    std::vector<uint8_t> packed (b200vf_gt_packed_bound (e->width, e->height));
-    size_t used = 0, raw_groups = 0;
-    rc = b200vf_gt_pack_index (idx.data (), e->width, e->height, packed.data (), packed.size (), &used, &raw_groups);
-    if (rc) return rc;
-    const size_t groups = (size_t) ((e->width + 127) / 128) * e->height;
-    if (raw_groups * 2 <= groups) {
-      rc = b200vf_malloc (e->ctx, used, &e->d_packed);
-      if (rc) return rc;
-      e->packed_cap = used;
-      B200VF_CHECK_CUDA (cudaMemcpyAsync (e->d_packed, packed.data (), used, cudaMemcpyHostToDevice, s));
-      B200VF_CHECK_CUDA (cudaStreamSynchronize (s));
-    }
-  }
   e->need_remap = false;
   return B200VF_OK;
 }
@@ -317,8 +297,6 @@ int run (b200vf_element *e, const uint8_t *d_in, uint8_t *d_out, int nframes, cu
         if (rc) return rc;
       }
       uint32_t fill = !strcmp (e->fmt->name, "AYUV") ? 0x808010ffu : 0u;     // GST_WRITE_UINT32_BE (.., 0xff108080), :244-250
-      if (e->d_packed && ((uintptr_t) d_in) % 4 == 0 && ((uintptr_t) d_out) % 16 == 0)
-        return b200vf_remap_packed (ctx, d_in, d_out, e->d_packed, w, h, e->in_bytes, nframes, fill, s);
       return b200vf_remap (ctx, d_in, d_out, e->d_index, w, h, e->fmt->pstride, e->in_stride, e->in_bytes, nframes, fill, s);
     }
   }
@@ -353,7 +331,6 @@ B200VF_API void b200vf_element_destroy (b200vf_element *e) {
   free_staging (e);
   for (int i = 0; i < kHostStreams; i++) if (e->hs[i]) cudaStreamDestroy (e->hs[i]);
   if (e->d_index) cudaFree (e->d_index);
-  if (e->d_packed) b200vf_free (e->ctx, e->d_packed);
   delete e;
 }
 

@@ -266,7 +266,8 @@ def test_factory_introspection_matches_reference_api_dump(vf):
 def test_packed_index_round_trips(vf):
     """b200vf_gt_pack_index is lossless for every map / off-edge policy / ragged width, and codes smooth maps almost fully"""
     rng = np.random.default_rng(7)
-    for (w, h) in [(300, 40), (128, 16), (100, 9), (257, 5)]:
+    r64 = lambda n: (n + 63) // 64 * 64
+    for (w, h) in [(300, 40), (128, 16), (100, 9), (257, 5), (5, 3)]:
         for el, plist in refprops.CASES.items():
             if el == "diffuse":
                 continue
@@ -275,26 +276,26 @@ def test_packed_index_round_trips(vf):
                 idx = vf.gt_resolve_map(m, w, h, off_edge)
                 packed, raw = vf.gt_pack_index(idx, w, h)
                 assert np.array_equal(vf.gt_unpack_index(packed, w, h), idx), (el, w, h, off_edge)
-                groups = ((w + 127) // 128) * h
-                assert 0 <= raw <= groups
-                assert packed.size == 64 + ((groups * 8 + 63) // 64) * 64 + groups * 128 + raw * 512
-    # a smooth map is coded completely; its table shrinks ~3.7x
+                chunks = ((w + 7) // 8) * h
+                assert 0 <= raw <= chunks
+                assert packed.size == 64 + r64(chunks * 4) + r64(chunks * 8) + raw * 32
+    # a smooth map is coded completely; its table shrinks ~2.6x
     w, h = 512, 64
     idx = vf.gt_resolve_map(vf.gt_build_map("fisheye", w, h), w, h, 1)
     packed, raw = vf.gt_pack_index(idx, w, h)
-    assert raw == 0 and packed.size < idx.nbytes / 3.5
+    assert raw == 0 and packed.size < idx.nbytes / 2.6
     # arbitrary tables (random targets, ignored pixels) survive too: everything goes raw
     idx = rng.integers(-1, w * h, (h, w), dtype=np.int32)
     packed, raw = vf.gt_pack_index(idx, w, h)
-    assert raw == ((w + 127) // 128) * h and np.array_equal(vf.gt_unpack_index(packed, w, h), idx)
+    assert raw == (w // 8) * h and np.array_equal(vf.gt_unpack_index(packed, w, h), idx)
     # steps at the coding limits (-8 .. +7 in both directions) are coded, one beyond is not
     base = 40 * w + 200
     row = base + np.cumsum(np.r_[0, np.tile([7, -8, 7 * w + 7, -8 * w - 8], 32)[:127]])
     idx = np.tile(np.r_[row, row, row, row].astype(np.int32), (h, 1))
     packed, raw = vf.gt_pack_index(idx, w, h)
-    assert raw == 0 and np.array_equal(vf.gt_unpack_index(packed, w, h), idx)
+    assert raw == 0 and np.array_equal(vf.gt_unpack_index(packed, w, h), idx)   # the jump back at each 128th pixel starts a chunk
     idx[3, 5] += 8 + 1                                   # dx = 7 -> 16 (and the next step -17)
-    packed, raw = vf.gt_pack_index(idx, w, h)
-    assert raw == 1 and np.array_equal(vf.gt_unpack_index(packed, w, h), idx)
+    packed2, raw2 = vf.gt_pack_index(idx, w, h)
+    assert raw2 == raw + 1 and np.array_equal(vf.gt_unpack_index(packed2, w, h), idx)
     with pytest.raises(vf.B200vfError):
-        vf.gt_unpack_index(packed[:-8], w, h)            # truncated blob
+        vf.gt_unpack_index(packed2[:-8], w, h)           # truncated blob

@@ -1,5 +1,5 @@
 """Runs one element kernel a few times (for ncu -k regex:... captures of kernels bench.py --profile does not reach).
-   python tools/run_one.py gaussblur|dilate|exclusion|chromahold|remap|lut4|direct [4k|8k]"""
+   python tools/run_one.py gaussblur|dilate|exclusion|chromahold|remap|remap_packed|lut4|direct [4k|8k]"""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gst-plugins-bad_b200"))
@@ -23,6 +23,10 @@ elif what == "lut4":
 elif what == "remap":
     idx = torch.from_numpy(b200vf.gt_resolve_map(b200vf.gt_build_map("fisheye", w, h), w, h, 1)).cuda()
     f = lambda: ctx.remap(a, b, idx, w, h, 4, 4 * w, nframes=n, stream=st)
+elif what == "remap_packed":
+    idx = b200vf.gt_resolve_map(b200vf.gt_build_map("fisheye", w, h), w, h, 1)
+    pk = torch.from_numpy(b200vf.gt_pack_index(idx, w, h)[0]).cuda()
+    f = lambda: ctx.remap_packed(a, b, pk, w, h, nframes=n, stream=st)
 elif what == "direct":
     src = torch.randint(0, 255, (8, h, w), dtype=torch.uint8, device="cuda"); dst = torch.empty((8, h, 4 * w), dtype=torch.uint8, device="cuda")
     ctx.set_variant("direct"); f = lambda: ctx.bayer2rgb(src, w, dst, 4 * w, w, h, 0, (0, 1, 2), nframes=8, stream=st)
