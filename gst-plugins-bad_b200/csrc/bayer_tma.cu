@@ -18,10 +18,8 @@
 // Needs: source base/pitch/frame pitch multiples of 16 B (TMA), destination
 // 16-byte aligned. Everything else goes to bayer2rgb_direct.
 #include "bayer.cuh"
-#include <cuda.h>
+#include "tma.cuh"
 #include <stdlib.h>
-
-int b200vf_next_tile_counter (b200vf_ctx *ctx, cudaStream_t s, unsigned int **out);
 
 namespace {
 
@@ -45,31 +43,6 @@ struct TmaParams {
   int tiles_x, tiles_y;
   int first_is_gr;
 };
-
-__device__ __forceinline__ uint32_t smem_u32 (const void *p) { return (uint32_t) __cvta_generic_to_shared (p); }
-
-__device__ __forceinline__ void mbar_init (uint64_t *bar, int count) {
-  asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx (uint64_t *bar, uint32_t bytes) {
-  asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32 (bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait (uint64_t *bar, uint32_t parity) {
-  asm volatile (
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" :: "r"(smem_u32 (bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d (void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
-  asm volatile (
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      :: "r"(smem_u32 (smem_dst)), "l"(map), "r"(smem_u32 (bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 
 __device__ __forceinline__ void tile_coords (int t, const TmaParams &p, int &f, int &ty, int &tx) {
   int per_frame = p.tiles_x * p.tiles_y;
@@ -148,7 +121,7 @@ bayer2rgb_tma_kernel (const __grid_constant__ CUtensorMap src_map, const TmaPara
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init (&full[s], 1); mbar_init (&empty[s], TMA_THREADS / 32); }
-    asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init ();
   }
   __syncthreads ();
 
@@ -163,7 +136,7 @@ bayer2rgb_tma_kernel (const __grid_constant__ CUtensorMap src_map, const TmaPara
         const int t = (int) atomicAdd (tile_counter, 1u);
         tile_of[s] = t < ntiles ? t : -1;                                  // -1: no more work
         if (t >= ntiles) {
-          asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (&full[s])) : "memory");
+          mbar_arrive (&full[s]);
           break;
         }
         int f, ty, tx;
@@ -235,7 +208,7 @@ bayer2rgb_tma_kernel (const __grid_constant__ CUtensorMap src_map, const TmaPara
       }
     }
     __syncwarp ();                                  // every lane is done reading stage s
-    if (lane == 0) asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (&empty[s])) : "memory");
+    if (lane == 0) mbar_arrive (&empty[s]);
   }
 }
 

@@ -3,6 +3,8 @@
 // work (8 B/px): 128-bit coalesced accesses, lane-replicated shared-memory tables
 // (entry v of lane l at word v*32+l: conflict-free for arbitrary data), no tensor cores.
 #include "common.cuh"
+#include "dilate.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -74,17 +76,7 @@ exclusion_kernel (const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t
 }
 
 // --------------------------------------------------------------------- dilate
-// gst/gaudieffects/gstdilate.c:258-345: best of {self, down, right, left} by luminance
-// 90 r + 115 g + 51 b, strict compare in that order (`up` is dead code, :291-294).
-__device__ __forceinline__ uint32_t dil_lum (uint32_t in) {
-  return __dp4a (in, 0x005a7333u, 0u);          // 51*b0 + 115*b1 + 90*b2 (+ 0*x): one IDP4A
-}
-template <bool ERODE>
-__device__ __forceinline__ void dil_pick_t (uint32_t &best, uint32_t &bl, uint32_t cand, uint32_t cl) {
-  const bool take = ERODE ? (cl < bl) : (cl > bl);
-  best = take ? cand : best;
-  bl = take ? cl : bl;
-}
+// arithmetic: dilate.cuh; TMA-fed fast path: dilate_tma.cu
 __device__ __forceinline__ void dil_pick (uint32_t &best, uint32_t &bl, uint32_t cand, uint32_t cl, bool erode) {
   if (erode) dil_pick_t<true> (best, bl, cand, cl); else dil_pick_t<false> (best, bl, cand, cl);
 }
@@ -402,7 +394,9 @@ Launch2D plan2d (b200vf_ctx *ctx, int width, int height, int row_stride, size_t 
   l.block = dim3 (256, 1, 1);
   int groups = (l.width + 3) / 4;
   int gx = (groups + 255) / 256;
-  int target = ctx->sm_count * 4;                 // 4 CTAs of 256 threads per SM (32 KB table each)
+  int per_sm = 4;                                 // CTAs of 256 threads per SM (32 KB table each)
+  if (const char *e = getenv ("B200VF_PLAN2D_CTAS_PER_SM")) { int v = atoi (e); if (v >= 1 && v <= 7) per_sm = v; }   // tuning knob
+  int target = ctx->sm_count * per_sm;
   int gy = 1;
   if (gx > target) gx = target;
   else { gy = target / gx; if (gy > l.height) gy = l.height; if (gy < 1) gy = 1; }
@@ -455,12 +449,34 @@ B200VF_API int b200vf_dilate (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_
   cudaStream_t s = b200vf_stream (ctx, stream);
   bool vec = (width % 4 == 0) && ((uintptr_t) d_src) % 16 == 0 && ((uintptr_t) d_dst) % 16 == 0 &&
       frame_stride % 16 == 0 && (!d_below || ((uintptr_t) d_below) % 16 == 0);
+  const bool tma = vec && frame_stride % 16 == 0 && ctx->variant != 1 && !getenv ("B200VF_DILATE_NO_TMA");
+  if (tma) {
+    // rows with a row under them inside d_src; a shard's last row takes `down` from d_below: direct kernel, 1 row
+    const int rows_tma = d_below ? height - 1 : height;
+    if (rows_tma > 0) {
+      int rc = b200vf_dilate_tma (ctx, d_src, d_dst, width, height, rows_tma, frame_stride, nframes, erode, s);
+      if (rc) return rc;
+    }
+    if (!d_below) return B200VF_OK;
+    const size_t last = (size_t) (height - 1) * width * 4;
+    dim3 block (32, 8);
+    dim3 grid ((width + 127) / 128, 1, nframes);
+    if (erode) dilate_kernel<true><<<grid, block, 0, s>>> (d_src + last, d_dst + last, width, 1, frame_stride, d_below);
+    else dilate_kernel<false><<<grid, block, 0, s>>> (d_src + last, d_dst + last, width, 1, frame_stride, d_below);
+    return b200vf_launched (ctx, "dilate");
+  }
   if (vec) {
     dim3 block (32, 8);
     int strips = (height + DIL_ROWS - 1) / DIL_ROWS;
     dim3 grid ((width + 127) / 128, (strips + 7) / 8, nframes);
-    if (erode) dilate_kernel<true><<<grid, block, 0, s>>> (d_src, d_dst, width, height, frame_stride, d_below);
-    else dilate_kernel<false><<<grid, block, 0, s>>> (d_src, d_dst, width, height, frame_stride, d_below);
+    int pad = 0;                                  // tuning knob: unused dynamic shared memory caps the resident CTAs per SM
+    if (const char *e = getenv ("B200VF_DILATE_SMEM_PAD_KB")) { int v = atoi (e); if (v >= 0 && v <= 200) pad = v * 1024; }
+    if (pad) {
+      B200VF_CHECK_CUDA (cudaFuncSetAttribute (dilate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+      B200VF_CHECK_CUDA (cudaFuncSetAttribute (dilate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+    }
+    if (erode) dilate_kernel<true><<<grid, block, pad, s>>> (d_src, d_dst, width, height, frame_stride, d_below);
+    else dilate_kernel<false><<<grid, block, pad, s>>> (d_src, d_dst, width, height, frame_stride, d_below);
     return b200vf_launched (ctx, "dilate");
   }
   dim3 grid ((width + 255) / 256, height, nframes);

@@ -96,6 +96,27 @@ def test_dilate(ctx, orc, rng, w, h, erode):
     assert np.array_equal(got, orc.dilate(src, erode)), ctx.last_kernel()
 
 
+@pytest.mark.parametrize("w,h", [(4, 2), (128, 32), (132, 33), (260, 70), (1024, 100), (3840, 64)])
+def test_dilate_tma_and_direct_paths(ctx, orc, rng, w, h):
+    """widths that are multiples of 4 take the TMA-fed kernel; `direct` forces the register-marching one: both exact"""
+    n = 2
+    src = rng.integers(0, 2 ** 32, (n, h, w), dtype=np.uint32)
+    src[:, ::3, ::5] = src[0, 0, 0]
+    d_src = ctx.upload(src)
+    d_dst = ctx.alloc(src.nbytes)
+    for erode in (False, True):
+        want = np.stack([orc.dilate(src[i], erode) for i in range(n)])
+        for variant, kernel in (("auto", "dilate_tma"), ("direct", "dilate")):
+            ctx.set_variant(variant)
+            try:
+                ctx.dilate(d_src, d_dst, w, h, erode, nframes=n)
+            finally:
+                ctx.set_variant("auto")
+            assert ctx.last_kernel() == kernel
+            got = ctx.download(d_dst, dtype=np.uint32).reshape(n, h, w)
+            assert np.array_equal(got, want), (variant, erode, np.argwhere(got != want)[:4])
+
+
 def test_dilate_batch_and_shard_below(ctx, orc, rng):
     w, h, n = 128, 32, 3
     src = rng.integers(0, 2 ** 32, (n, h, w), dtype=np.uint32)
