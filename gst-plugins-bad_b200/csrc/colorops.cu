@@ -4,6 +4,7 @@
 // (entry v of lane l at word v*32+l: conflict-free for arbitrary data), no tensor cores.
 #include "common.cuh"
 #include "dilate.cuh"
+#include "stream.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -42,6 +43,12 @@ __device__ __forceinline__ uint32_t excl_px (const uint32_t *tl, uint32_t in, ui
   int r2 = clamp255 (f - (int) ((wr >> 16) + q));
   return (wb & 0xff) | ((wg & 0xff) << 8) | ((uint32_t) r2 << 16);
 }
+
+struct ExclOp {                          // stream.cuh operator
+  ExclParams p;
+  __device__ __forceinline__ void fill (uint32_t *tab) const { table_fill (tab, p.t); }
+  __device__ __forceinline__ uint32_t apply (const uint32_t *tl, uint32_t px) const { return excl_px (tl, px, p.magic, p.factor); }
+};
 
 __global__ void __launch_bounds__ (512)
 exclusion_kernel (const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n16,
@@ -206,6 +213,15 @@ __device__ __forceinline__ uint32_t ce_ayuv_px (const uint32_t *tl, uint32_t in,
   return (in & p.keep_mask) | ((uint32_t) y2 << p.sr) | ((uint32_t) u2 << p.sg) | ((uint32_t) v2 << p.sb);
 }
 
+template <bool AYUV>
+struct ColorOp {                         // stream.cuh operator
+  ColorParams p;
+  __device__ __forceinline__ void fill (uint32_t *tab) const { table_fill (tab, p.t); }
+  __device__ __forceinline__ uint32_t apply (const uint32_t *tl, uint32_t px) const {
+    return AYUV ? ce_ayuv_px (tl, px, p) : ce_rgb_px (tl, px, p);
+  }
+};
+
 // 4-byte pixels; a row is `width` pixels at data + y*row_stride (rows 4-byte aligned).
 template <bool AYUV>
 __global__ void __launch_bounds__ (256)
@@ -333,6 +349,12 @@ __device__ __forceinline__ uint32_t ch_px (const uint32_t *tl, uint32_t in, cons
   return in;
 }
 
+struct ChromaOp {                        // stream.cuh operator
+  ChromaParams p;
+  __device__ __forceinline__ void fill (uint32_t *tab) const { table_fill (tab, p.t); }
+  __device__ __forceinline__ uint32_t apply (const uint32_t *tl, uint32_t px) const { return ch_px (tl, px, p); }
+};
+
 __global__ void __launch_bounds__ (256)
 chromahold_kernel (uint8_t *data, int width, int height, int row_stride, size_t frame_stride,
     const __grid_constant__ ChromaParams p)
@@ -381,6 +403,17 @@ chromahold_kernel (uint8_t *data, int width, int height, int row_stride, size_t 
 // A contiguous batch (row_stride == 4*width, frames back to back) is flattened to
 // one long row so every access is a full 128-bit vector.
 struct Launch2D { dim3 grid, block; int width, height, row_stride; size_t frame_stride; int nframes; };
+
+// contiguous frames of 4-byte pixels whose bytes form one 16-byte aligned stream: the TMA ring takes them
+bool flat_stream (const b200vf_ctx *ctx, const uint8_t *data, int width, int height, int row_stride, size_t frame_stride,
+    int nframes, size_t *nbytes) {
+  if (!stream_enabled (ctx) || row_stride != 4 * width) return false;
+  if (nframes > 1 && frame_stride != (size_t) row_stride * height) return false;
+  const size_t n = (size_t) row_stride * height * nframes;
+  if (((uintptr_t) data) % 16 != 0 || n % 16 != 0 || n < 16384) return false;
+  *nbytes = n;
+  return true;
+}
 
 Launch2D plan2d (b200vf_ctx *ctx, int width, int height, int row_stride, size_t frame_stride, int nframes, int pstride) {
   Launch2D l;
@@ -431,6 +464,15 @@ B200VF_API int b200vf_exclusion (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t 
   if (!attr) { B200VF_CHECK_CUDA (cudaFuncSetAttribute (exclusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAB_SMEM)); attr = true; }
   size_t n16 = npix_total / 4;
   int ntail = (int) (npix_total - n16 * 4);
+  if (stream_enabled (ctx) && n16 >= 1024) {
+    ExclOp op;
+    op.p = p;
+    int rc = stream_launch (ctx, d_src, d_dst, n16 * 16, op, b200vf_stream (ctx, stream), "exclusion_tma");
+    if (rc || !ntail) return rc;
+    exclusion_kernel<<<1, 512, TAB_SMEM, b200vf_stream (ctx, stream)>>> (nullptr, nullptr, 0,
+        reinterpret_cast<const uint32_t *> (d_src) + n16 * 4, reinterpret_cast<uint32_t *> (d_dst) + n16 * 4, ntail, p);
+    return b200vf_launched (ctx, "exclusion_tail");
+  }
   int grid = ctx->sm_count * 2;
   size_t need = (n16 + 511) / 512;
   if (need < (size_t) grid) grid = need ? (int) need : 1;
@@ -514,6 +556,12 @@ B200VF_API int b200vf_coloreffects_rgb (b200vf_ctx *ctx, uint8_t *d_data, int wi
     p.map_luma = map_luma;
     for (int v = 0; v < 256; v++)
       p.t.w[v] = ((uint32_t) table768[3 * v] << p.sr) | ((uint32_t) table768[3 * v + 1] << p.sg) | ((uint32_t) table768[3 * v + 2] << p.sb);
+    size_t nbytes;
+    if (flat_stream (ctx, d_data, width, height, row_stride, frame_stride, nframes, &nbytes)) {
+      ColorOp<false> op;
+      op.p = p;
+      return stream_launch (ctx, d_data, d_data, nbytes, op, s, "coloreffects_rgb4_tma", 16);
+    }
     Launch2D l = plan2d (ctx, width, height, row_stride, frame_stride, nframes, 4);
     coloreffects4_kernel<false><<<l.grid, l.block, TAB_SMEM, s>>> (d_data, l.width, l.height, l.row_stride, l.frame_stride, p);
     return b200vf_launched (ctx, "coloreffects_rgb4");
@@ -549,6 +597,12 @@ B200VF_API int b200vf_coloreffects_ayuv (b200vf_ctx *ctx, uint8_t *d_data, int w
   p.map_luma = map_luma;
   for (int v = 0; v < 256; v++)      // R,G,B of the table in bytes 0,1,2 (the matrices need them as numbers)
     p.t.w[v] = (uint32_t) table768[3 * v] | ((uint32_t) table768[3 * v + 1] << 8) | ((uint32_t) table768[3 * v + 2] << 16);
+  size_t nbytes;
+  if (flat_stream (ctx, d_data, width, height, row_stride, frame_stride, nframes, &nbytes)) {
+    ColorOp<true> op;
+    op.p = p;
+    return stream_launch (ctx, d_data, d_data, nbytes, op, b200vf_stream (ctx, stream), "coloreffects_ayuv_tma", 16);
+  }
   Launch2D l = plan2d (ctx, width, height, row_stride, frame_stride, nframes, 4);
   coloreffects4_kernel<true><<<l.grid, l.block, TAB_SMEM, b200vf_stream (ctx, stream)>>> (d_data, l.width, l.height,
       l.row_stride, l.frame_stride, p);
@@ -592,6 +646,12 @@ B200VF_API int b200vf_chromahold (b200vf_ctx *ctx, uint8_t *d_data, int width, i
   }
   p.t.w[0] = p.t.w[1] = 0;
   for (int c = 2; c < 256; c++) p.t.w[c] = (uint32_t) (0x100000000ull / (uint64_t) c) + 1u;
+  size_t nbytes;
+  if (flat_stream (ctx, d_data, width, height, row_stride, frame_stride, nframes, &nbytes)) {
+    ChromaOp op;
+    op.p = p;
+    return stream_launch (ctx, d_data, d_data, nbytes, op, b200vf_stream (ctx, stream), "chromahold_tma", 16);
+  }
   Launch2D l = plan2d (ctx, width, height, row_stride, frame_stride, nframes, 4);
   chromahold_kernel<<<l.grid, l.block, TAB_SMEM, b200vf_stream (ctx, stream)>>> (d_data, l.width, l.height,
       l.row_stride, l.frame_stride, p);

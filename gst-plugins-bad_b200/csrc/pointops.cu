@@ -12,6 +12,7 @@
 // random lookups always hit 32 different banks (no conflicts for random data),
 // and one word carries the four channel tables, so a lookup is one LDS.32.
 #include "lut.cuh"
+#include "stream.cuh"
 #include <math.h>
 #include <string.h>
 
@@ -49,6 +50,12 @@ lut4_kernel (const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n16,
   }
   if (blockIdx.x == 0 && threadIdx.x < ntail) dst_tail[threadIdx.x] = lut_px (tl, src_tail[threadIdx.x]);
 }
+
+struct LutOp {                           // stream.cuh operator: the same table, the same lookup
+  PackedLut lut;
+  __device__ __forceinline__ void fill (uint32_t *tab) const { lut_fill (tab, lut); }
+  __device__ __forceinline__ uint32_t apply (const uint32_t *tl, uint32_t px) const { return lut_px (tl, px); }
+};
 
 }  // namespace
 
@@ -92,15 +99,29 @@ B200VF_API int b200vf_lut4 (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_ds
     }
     return B200VF_OK;
   }
-  int grid = b200vf_persistent_grid (ctx, 2);
-  size_t need = (body + LUT_THREADS - 1) / LUT_THREADS;
-  if (need < (size_t) grid) grid = need ? (int) need : 1;
   int ntail = (int) (npix_total - done);
-  // head pixels (if any) ride along as an extra tiny launch only when present
-  lut4_kernel<<<grid, LUT_THREADS, smem, s>>> (reinterpret_cast<const uint4 *> (d_src + 4 * head),
-      reinterpret_cast<uint4 *> (d_dst + 4 * head), body, s32 + done, d32 + done, ntail, p);
-  int rc = b200vf_launched (ctx, "lut4");
-  if (rc) return rc;
+  int rc;
+  if (stream_enabled (ctx) && body >= 1024) {
+    // TMA-fed ring (stream.cuh) over the 16-byte aligned body; the <= 3 tail pixels go with the head launch below
+    LutOp op;
+    op.lut = p;
+    rc = stream_launch (ctx, d_src + 4 * head, d_dst + 4 * head, body * 16, op, s, "lut4_tma", 8);
+    if (rc) return rc;
+    if (ntail) {
+      lut4_kernel<<<1, LUT_THREADS, smem, s>>> (nullptr, nullptr, 0, s32 + done, d32 + done, ntail, p);
+      rc = b200vf_launched (ctx, "lut4_tail");
+      if (rc) return rc;
+    }
+  } else {
+    int grid = b200vf_persistent_grid (ctx, 2);
+    size_t need = (body + LUT_THREADS - 1) / LUT_THREADS;
+    if (need < (size_t) grid) grid = need ? (int) need : 1;
+    // head pixels (if any) ride along as an extra tiny launch only when present
+    lut4_kernel<<<grid, LUT_THREADS, smem, s>>> (reinterpret_cast<const uint4 *> (d_src + 4 * head),
+        reinterpret_cast<uint4 *> (d_dst + 4 * head), body, s32 + done, d32 + done, ntail, p);
+    rc = b200vf_launched (ctx, "lut4");
+    if (rc) return rc;
+  }
   if (head) {
     lut4_kernel<<<1, LUT_THREADS, smem, s>>> (nullptr, nullptr, 0, s32, d32, (int) head, p);
     rc = b200vf_launched (ctx, "lut4_head");

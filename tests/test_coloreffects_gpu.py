@@ -92,3 +92,26 @@ def test_chromahold_all_hues(ctx, orc):
         d = ctx.upload(fr)
         ctx.chromahold(d, w, h, 4 * w, RGB_OFFSETS["RGBA"], (40, 200, 90), tol)
         assert np.array_equal(ctx.download(d).reshape(fr.shape), orc.chromahold(fr, w, h, "RGBA", (40, 200, 90), tol))
+
+
+@pytest.mark.parametrize("w,h,n", [(64, 64, 1), (640, 480, 1), (100, 41, 3), (1000, 33, 2)])
+def test_tma_ring_and_grid_stride_paths(ctx, vf, orc, rng, w, h, n):
+    """contiguous 4-byte frames of >= 16 KB stream through the TMA ring (stream.cuh); `direct` forces the
+    grid-stride kernels: same bytes from both, in place"""
+    fr = rng.integers(0, 256, (n * h, w * 4), dtype=np.uint8)
+    for variant, suffix in (("auto", "_tma"), ("direct", "")):
+        ctx.set_variant(variant)
+        try:
+            for fmt, preset in (("BGRx", "sepia"), ("RGBA", "xpro"), ("AYUV", "heat"), ("AYUV", "yellowblue")):
+                got = run_ce(ctx, vf, fr, w, h, fmt, preset, nframes=n).reshape(n, h, w * 4)
+                assert ctx.last_kernel().endswith("_tma") == (suffix == "_tma"), ctx.last_kernel()
+                for i in range(n):
+                    assert np.array_equal(got[i], orc.coloreffects(fr[i * h:(i + 1) * h], w, h, fmt, preset)), (variant, fmt, preset)
+            d = ctx.upload(fr)
+            ctx.chromahold(d, w, h, 4 * w, RGB_OFFSETS["xRGB"], (0, 200, 30), 30, nframes=n)
+            assert ctx.last_kernel() == "chromahold" + suffix
+            got = ctx.download(d).reshape(n, h, w * 4)
+            for i in range(n):
+                assert np.array_equal(got[i], orc.chromahold(fr[i * h:(i + 1) * h], w, h, "xRGB", (0, 200, 30), 30))
+        finally:
+            ctx.set_variant("auto")

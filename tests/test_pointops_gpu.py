@@ -132,3 +132,28 @@ def test_dilate_batch_and_shard_below(ctx, orc, rng):
     ctx.dilate(d_src, d_dst, w, 20, False, nframes=1, below=d_below)
     got = ctx.download(d_dst, dtype=np.uint32)[: 20 * w].reshape(20, w)
     assert np.array_equal(got, full[:20])
+
+
+@pytest.mark.parametrize("n", [4096, 4099, 70001, (1 << 20) + 7])
+def test_point_ops_tma_ring_and_grid_stride_paths(ctx, orc, vf, rng, n):
+    """from 1024 16-byte groups on, lut4 and exclusion stream through the TMA ring (stream.cuh);
+    `direct` forces the grid-stride kernels. Both bit-exact, ragged sizes included."""
+    src = rng.integers(0, 2 ** 32, n, dtype=np.uint32)
+    d_src = ctx.upload(src)
+    d_dst = ctx.alloc(src.nbytes)
+    for variant, k_lut, k_ex in (("auto", "lut4_t", "exclusion_t"), ("direct", "lut4", "exclusion")):
+        ctx.set_variant(variant)
+        try:
+            ctx.lut4(d_src, d_dst, n, vf.lut_burn(175))
+            assert ctx.last_kernel().startswith(k_lut), ctx.last_kernel()
+            got = ctx.download(d_dst, dtype=np.uint32)
+            assert np.array_equal(got, orc.burn(src, 175)), variant
+            ctx.exclusion(d_src, d_dst, n, 100)
+            assert ctx.last_kernel().startswith(k_ex), ctx.last_kernel()
+            got = ctx.download(d_dst, dtype=np.uint32)
+            assert np.array_equal(got, orc.exclusion(src, 100)), variant
+        finally:
+            ctx.set_variant("auto")
+    # in place (dst == src) through the ring: a chunk is written back only after it was copied out
+    ctx.lut4(d_src, d_src, n, vf.lut_burn(175))
+    assert np.array_equal(ctx.download(d_src, dtype=np.uint32), orc.burn(src, 175))
