@@ -400,8 +400,14 @@ def side_measurements(ctx, torch, b200vf, st, side, peak):
         n4 = max(2, min(n, int(3e9 // (px * 8))))
         a = dst[:n4]
         b = torch.empty_like(a)
-        t = timeit(lambda: ctx.lut4(a, b, n4 * px, b200vf.lut_burn(175), stream=st))
+        burn = b200vf.lut_burn(175)
+        t = timeit(lambda: ctx.lut4(a, b, n4 * px, burn, stream=st))
         rec("burn_lut4_%s" % tag, n4, px, 8, t)
+        # rgb2bayer: 4 B read + 1 B written per pixel
+        mosaic = torch.empty((n4, h, w), dtype=torch.uint8, device="cuda")
+        t = timeit(lambda: ctx.rgb2bayer(a, 4 * w, mosaic, w, w, h, 0, nframes=n4, stream=st))
+        rec("rgb2bayer_%s" % tag, n4, px, 5, t)
+        del mosaic
         t = timeit(lambda: ctx.exclusion(a, b, n4 * px, 175, stream=st))
         rec("exclusion_%s" % tag, n4, px, 8, t)
         t = timeit(lambda: ctx.dilate(a, b, w, h, False, nframes=n4, stream=st))

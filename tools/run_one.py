@@ -7,7 +7,7 @@ import torch, b200vf
 what = sys.argv[1]; size = sys.argv[2] if len(sys.argv) > 2 else "4k"
 w, h = (3840, 2160) if size == "4k" else (7680, 4320)
 ctx = b200vf.Context(0); side = torch.cuda.Stream(); torch.cuda.set_stream(side); st = side.cuda_stream
-n = 2
+n = 2 if (what == "gaussblur" or size == "8k") else 8          # point ops: a batch larger than L2
 a = torch.randint(0, 255, (n, h, 4 * w), dtype=torch.uint8, device="cuda"); b = torch.empty_like(a)
 if what == "gaussblur":
     k, ks = b200vf.gauss_kernel(5.0)
