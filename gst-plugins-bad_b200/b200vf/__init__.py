@@ -73,6 +73,7 @@ _SIGS = {
     "b200vf_gauss_kernel": (_i, [C.c_float, _vp, _vp, _i]),
     "b200vf_gaussblur": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _sz, _i, _i, _vp, _vp, _i, _i, _vp]),
     "b200vf_gauss_selftest_div": (_i, [_vp, C.c_float, C.c_uint32, C.c_uint32, _vp]),
+    "b200vf_gauss_selftest_finish": (_i, [_vp, C.c_uint32, C.c_uint32, _vp]),
     "b200vf_coloreffects_table": (_i, [_i, C.POINTER(_vp), C.POINTER(_i)]),
     "b200vf_coloreffects_rgb": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "b200vf_coloreffects_ayuv": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _i, _i, _vp, _i, _vp]),
@@ -272,6 +273,12 @@ class Context:
         """mismatches between the blur's reciprocal-based division and IEEE a / divisor over fp32 bit patterns"""
         bad = C.c_ulonglong(0)
         check(lib.b200vf_gauss_selftest_div(self.h, float(divisor), int(lo_bits), int(hi_bits), C.byref(bad)))
+        return bad.value
+
+    def gauss_selftest_finish(self, lo_bits=0, hi_bits=0xffffffff):
+        """mismatches between the blur's fp32-only final rounding and (guint8) CLAMP (q + 0.5 [fp64], 0, 255)"""
+        bad = C.c_ulonglong(0)
+        check(lib.b200vf_gauss_selftest_finish(self.h, int(lo_bits), int(hi_bits), C.byref(bad)))
         return bad.value
 
     def coloreffects_rgb(self, data, width, height, row_stride, pixel_stride, offs, table, map_luma, nframes=1,

@@ -183,6 +183,12 @@ int b200vf_gaussblur (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, int
  * (must be 0 over the range the host enables it for, see gaussblur.cu div_rn). */
 int b200vf_gauss_selftest_div (b200vf_ctx *ctx, float divisor, uint32_t lo_bits, uint32_t hi_bits,
     unsigned long long *mismatches);
+/* Test hook: the blur's last step, (guint8) CLAMP (q + 0.5 [double], 0, 255)
+ * (gstgaussblur.c:348-351), is computed without fp64; this counts the fp32 bit
+ * patterns q in [lo_bits, hi_bits] (inclusive) for which it differs from the
+ * fp64 expression (0 .. 0xffffffff covers all of fp32; must be 0). */
+int b200vf_gauss_selftest_finish (b200vf_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits,
+    unsigned long long *mismatches);
 
 /* ------------------------------------------------------- coloreffects plugin
  * In place (transform_frame_ip, gstcoloreffects.c:479-501).

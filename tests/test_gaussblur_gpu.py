@@ -18,13 +18,55 @@ def run(ctx, vf, frame, w, h, sigma, p0, exact=True):
 
 
 @pytest.mark.parametrize("sigma", [-5, -1.2, 0, 0.3, 1.2, 5, 20])
-@pytest.mark.parametrize("p0", [0, 1, 2])
+@pytest.mark.parametrize("p0", [0, 1, 2, 3])
 def test_sigmas_small_frames(ctx, vf, orc, rng, sigma, p0):
     for (w, h) in [(8, 8), (40, 30), (70, 66)]:      # 8x8 at sigma=5: both edges truncate at once; 70x66: > one tile
         fr = frames.random_u8(rng, h, 4 * w)
         got = run(ctx, vf, fr, w, h, sigma, p0)
         want = orc.gaussblur(fr, w, h, sigma, p0)
         assert np.array_equal(got, want), (sigma, p0, w, h, ctx.last_kernel(), np.abs(got.astype(int) - want).max(), np.argwhere(got != want)[:4])
+
+
+@pytest.mark.parametrize("gth,ctas", [(8, 1), (8, 3), (12, 2), (32, 5), (64, 4)])
+@pytest.mark.parametrize("sigma,p0", [(5, 1), (1.2, 0), (12.5, 3), (-5, 2)])
+def test_strip_walk_carries_rows_between_steps(ctx, vf, orc, rng, monkeypatch, gth, ctas, sigma, p0):
+    """A CTA owns a contiguous range of (strip, step) units and MOVES the last 2*center fp32 rows of a step to
+    the top of its tile for the next one. Few CTAs and short steps (tuning knobs of the library) make every
+    case of that walk happen on a small frame: ranges that start in mid-strip, ranges that span strips and
+    frames, halos longer than a step (moved in several batches), a last step shorter than the others."""
+    monkeypatch.setenv("B200VF_GAUSS_GTH", str(gth))
+    monkeypatch.setenv("B200VF_GAUSS_CTAS", str(ctas))
+    w, h, n = 75, 150, 2
+    fr = frames.random_u8(rng, n * h, 4 * w)
+    k, ks = vf.gauss_kernel(sigma)
+    d_src = ctx.upload(fr)
+    d_dst = ctx.alloc(fr.size + 64)
+    ctx.gaussblur(d_src, d_dst, w, h, 4 * w, p0, k, ks, nframes=n)
+    got = ctx.download(d_dst, fr.size).reshape(n, h, 4 * w)
+    for i in range(n):                 # frames of a batch are independent: bytes past a frame read as 0 (D5 slack)
+        want = orc.gaussblur(fr[i * h:(i + 1) * h], w, h, sigma, p0)
+        assert np.array_equal(got[i], want), (i, np.argwhere(got[i] != want)[:6])
+    # the knobs must not change a byte: same call with the default schedule
+    monkeypatch.delenv("B200VF_GAUSS_GTH")
+    monkeypatch.delenv("B200VF_GAUSS_CTAS")
+    d_ref = ctx.alloc(fr.size + 64)
+    ctx.gaussblur(d_src, d_ref, w, h, 4 * w, p0, k, ks, nframes=n)
+    assert np.array_equal(ctx.download(d_ref, fr.size).reshape(n, h, 4 * w), got)
+
+
+def test_mid_size_frame_many_units_per_cta(ctx, vf, orc, rng):
+    """1024x1300: 33 strips x 21 steps = 693 units on <= 296 CTAs, the default schedule with carried rows"""
+    w, h = 1024, 1300
+    fr = frames.random_u8(rng, h, 4 * w)
+    for sigma, p0 in [(5, 1), (2.0, 0)]:
+        got = run(ctx, vf, fr, w, h, sigma, p0)
+        want = orc.gaussblur(fr, w, h, sigma, p0)
+        assert np.array_equal(got, want), (sigma, p0, np.argwhere(got != want)[:6])
+
+
+def test_final_rounding_all_fp32(ctx):
+    """(guint8) CLAMP (q + 0.5 [fp64], 0, 255) computed without fp64 (finish_bits / finish_u8): every fp32 q"""
+    assert ctx.gauss_selftest_finish(0, 0xffffffff) == 0
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
