@@ -27,16 +27,17 @@ def test_sigmas_small_frames(ctx, vf, orc, rng, sigma, p0):
         assert np.array_equal(got, want), (sigma, p0, w, h, ctx.last_kernel(), np.abs(got.astype(int) - want).max(), np.argwhere(got != want)[:4])
 
 
-@pytest.mark.parametrize("gth,ctas", [(8, 1), (8, 3), (12, 2), (32, 5), (64, 4)])
+@pytest.mark.parametrize("gth,ctas", [(8, 1), (8, 3), (16, 2), (32, 5), (64, 4)])
 @pytest.mark.parametrize("sigma,p0", [(5, 1), (1.2, 0), (12.5, 3), (-5, 2)])
-def test_strip_walk_carries_rows_between_steps(ctx, vf, orc, rng, monkeypatch, gth, ctas, sigma, p0):
+@pytest.mark.parametrize("w", [75, 76])          # rows of 300 B (pre-pass route) and of 304 B (16-byte aligned: TMA reads the frame itself)
+def test_strip_walk_carries_rows_between_steps(ctx, vf, orc, rng, monkeypatch, gth, ctas, sigma, p0, w):
     """A CTA owns a contiguous range of (strip, step) units and MOVES the last 2*center fp32 rows of a step to
     the top of its tile for the next one. Few CTAs and short steps (tuning knobs of the library) make every
     case of that walk happen on a small frame: ranges that start in mid-strip, ranges that span strips and
     frames, halos longer than a step (moved in several batches), a last step shorter than the others."""
     monkeypatch.setenv("B200VF_GAUSS_GTH", str(gth))
     monkeypatch.setenv("B200VF_GAUSS_CTAS", str(ctas))
-    w, h, n = 75, 150, 2
+    h, n = 150, 2
     fr = frames.random_u8(rng, n * h, 4 * w)
     k, ks = vf.gauss_kernel(sigma)
     d_src = ctx.upload(fr)
@@ -62,6 +63,24 @@ def test_mid_size_frame_many_units_per_cta(ctx, vf, orc, rng):
         got = run(ctx, vf, fr, w, h, sigma, p0)
         want = orc.gaussblur(fr, w, h, sigma, p0)
         assert np.array_equal(got, want), (sigma, p0, np.argwhere(got != want)[:6])
+
+
+@pytest.mark.parametrize("p0", [1, 2, 3])
+@pytest.mark.parametrize("pad", [0, 16])
+def test_aligned_view_equals_prepass_route_and_oracle(ctx, vf, orc, rng, monkeypatch, p0, pad):
+    """16-byte aligned rows are blurred in place as aligned words (byte offset p0 handled at the frame's left and
+    right edge only; unpadded rows fetch column w from the next row, padded rows find it in the padding);
+    other pitches go through the realigning pre-pass. Both must give the reference's bytes."""
+    w, h = 160, 140
+    fr = frames.random_u8(rng, h, 4 * w + pad)
+    for sigma in (5, 1.2):
+        want = orc.gaussblur(fr, w, h, sigma, p0)
+        got = run(ctx, vf, fr, w, h, sigma, p0)
+        assert np.array_equal(got, want), ("aligned view", sigma, np.argwhere(got != want)[:6])
+        monkeypatch.setenv("B200VF_GAUSS_PREPASS", "1")
+        got2 = run(ctx, vf, fr, w, h, sigma, p0)
+        monkeypatch.delenv("B200VF_GAUSS_PREPASS")
+        assert np.array_equal(got2, want), ("pre-pass", sigma, np.argwhere(got2 != want)[:6])
 
 
 def test_final_rounding_all_fp32(ctx):
