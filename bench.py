@@ -417,18 +417,24 @@ def side_measurements(ctx, torch, b200vf, st, side, peak):
         rec("coloreffects_sepia_%s" % tag, n4, px, 8, t)
         t = timeit(lambda: ctx.chromahold(b, w, h, 4 * w, (0, 1, 2), (255, 0, 0), 30, nframes=n4, stream=st))
         rec("chromahold_%s" % tag, n4, px, 8, t)
-        # gaussianblur sigma=5 (27 taps): FP32-issue bound; report vs both rooflines
+        # gaussianblur sigma=5 (27 taps): FP32-issue bound; report vs both rooflines.
+        # p0 = byte offset of component 0: 1 = AYUV (what the element negotiates), 2 = BGRx
+        # (BASELINE.json configs[2] names that layout), 0 = RGBx.
         k, ks = b200vf.gauss_kernel(5.0)
         ng = 4
-        for exact in (1, 0):
-            t = timeit(lambda: ctx.gaussblur(a, b, w, h, 4 * w, 1, k, ks, exact=bool(exact), nframes=ng, stream=st), iters=3)
-            flops = 16 * len(k) * px * ng
-            # FP32 roofline: 148 SMs x 128 lanes x 1.965 GHz = 37.2 T lane-op/s; packed f32x2 ops issue at half
-            # rate on B200 (measured, tools/probe/fp_probe.cu), so they do not raise it. exact = mul + add per tap.
-            fp32_peak = 148 * 128 * 1.965e9
-            rec("gaussblur_sigma5_%s_%s" % (tag, "exact" if exact else "fma"), ng, px, 8, t,
-                {"fp32_ops_per_s": flops / t, "frac_fp32": (flops if exact else flops / 2) / t / fp32_peak,
-                 "bound": "fp32 issue, not HBM (SURVEY D6)"})
+        # FP32 roofline: 148 SMs x 128 lanes x 1.965 GHz = 37.2 T lane-op/s; packed f32x2 ops issue at half
+        # rate on B200 (measured, tools/probe/fp_probe.cu), so they do not raise it. exact = mul + add per tap.
+        fp32_peak = 148 * 128 * 1.965e9
+        for p0, layout in ((1, "ayuv"), (2, "bgrx"), (0, "rgbx")):
+            for exact in (1, 0):
+                if p0 != 1 and not exact:
+                    continue
+                t = timeit(lambda: ctx.gaussblur(a, b, w, h, 4 * w, p0, k, ks, exact=bool(exact), nframes=ng, stream=st), iters=5)
+                flops = 16 * len(k) * px * ng
+                name = "gaussblur_sigma5_%s_%s" % (tag, "exact" if exact else "fma") + ("" if p0 == 1 else "_" + layout)
+                rec(name, ng, px, 8, t,
+                    {"p0": p0, "fp32_ops_per_s": flops / t, "frac_fp32": (flops if exact else flops / 2) / t / fp32_peak,
+                     "bound": "fp32 issue, not HBM (SURVEY D6)"})
         if tag == "8k":
             # BASELINE.json configs[3]: fisheye 7680x4320 RGBA (nearest-neighbour gather, index table)
             t0 = time.perf_counter()

@@ -266,13 +266,19 @@ B200VF_API int b200vf_bayer2rgb_shard_fused (b200vf_ctx *ctx, const uint8_t *d_s
 
 // ------------------------------------------------------------------ rgb2bayer
 // gst/bayer/gstrgb2bayer.c:254-267: dest[i] = byte 3 / 1 / 2 of the ARGB pixel
-// depending on (row, column) parity vs the pattern. 4 pixels per lane.
+// depending on (row, column) parity vs the pattern. HBM-bound (4 B read, 1 B written per
+// pixel): a lane owns 16 pixels of a row - four independent 128-bit streaming loads in
+// flight, one PRMT per pixel pair, one 128-bit store.
 namespace {
+__device__ __forceinline__ uint32_t rgb2bayer_pick4 (uint4 v, uint32_t sel_pair) {
+  // bytes (even pixel, odd pixel) of two pixel pairs -> 4 mosaic bytes
+  return PRMT (PRMT (v.x, v.y, sel_pair), PRMT (v.z, v.w, sel_pair), 0x5410);
+}
 __global__ void __launch_bounds__ (256)
 rgb2bayer_kernel (const uint8_t *src, int src_stride, size_t src_fs, uint8_t *dst, int dst_stride, size_t dst_fs,
     int width, int height, int pattern)
 {
-  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (x0 >= width || j >= height) return;
   const uint8_t *sp = src + (size_t) blockIdx.z * src_fs + (size_t) j * src_stride + (size_t) x0 * 4;
@@ -284,12 +290,12 @@ rgb2bayer_kernel (const uint8_t *src, int src_stride, size_t src_fs, uint8_t *ds
     int is_blue = ((j & 1) << 1) | par;
     sel[par] = (is_blue == pattern) ? 3 : (((is_blue ^ 3) == pattern) ? 1 : 2);
   }
-  int n = min (4, width - x0);
-  if (n == 4 && (((uintptr_t) sp) & 15) == 0) {
-    uint4 v = ld_stream_v4 (sp);
-    uint32_t e0 = (v.x >> (8 * sel[0])) & 0xff, o0 = (v.y >> (8 * sel[1])) & 0xff;
-    uint32_t e1 = (v.z >> (8 * sel[0])) & 0xff, o1 = (v.w >> (8 * sel[1])) & 0xff;
-    *reinterpret_cast<uint32_t *> (dp) = e0 | (o0 << 8) | (e1 << 16) | (o1 << 24);
+  const int n = min (16, width - x0);
+  if (n == 16 && (((uintptr_t) sp) & 15) == 0 && (((uintptr_t) dp) & 15) == 0) {
+    const uint32_t sel_pair = (uint32_t) sel[0] | ((uint32_t) (4 + sel[1]) << 4);     // byte 0 <- even pixel, byte 1 <- odd pixel
+    const uint4 v0 = ld_stream_v4 (sp), v1 = ld_stream_v4 (sp + 16), v2 = ld_stream_v4 (sp + 32), v3 = ld_stream_v4 (sp + 48);
+    st_stream_v4 (dp, make_uint4 (rgb2bayer_pick4 (v0, sel_pair), rgb2bayer_pick4 (v1, sel_pair),
+        rgb2bayer_pick4 (v2, sel_pair), rgb2bayer_pick4 (v3, sel_pair)));
   } else {
     for (int i = 0; i < n; i++) dp[i] = sp[4 * i + sel[i & 1]];
   }
@@ -305,8 +311,8 @@ B200VF_API int b200vf_rgb2bayer (b200vf_ctx *ctx, const uint8_t *d_src, int src_
   B200VF_REQUIRE (src_stride >= 4 * width && dst_stride >= width, B200VF_E_INVAL, "rgb2bayer: strides");
   B200VF_REQUIRE (dst_stride % 4 == 0 && ((uintptr_t) d_dst) % 4 == 0 && dst_frame_stride % 4 == 0, B200VF_E_INVAL,
       "rgb2bayer: destination pitch/base must be 4-byte aligned");
-  dim3 block (64, 4);
-  dim3 grid ((width + 255) / 256, (height + 3) / 4, nframes);
+  dim3 block (64, 4);                                      // 1024 pixels x 4 rows per CTA
+  dim3 grid ((width + 1023) / 1024, (height + 3) / 4, nframes);
   rgb2bayer_kernel<<<grid, block, 0, b200vf_stream (ctx, stream)>>> (d_src, src_stride, src_frame_stride,
       d_dst, dst_stride, dst_frame_stride, width, height, pattern);
   return b200vf_launched (ctx, "rgb2bayer");

@@ -112,3 +112,38 @@ def test_row_shards_equal_whole_frame(ctx, orc, rng, w, h, cuts, variant):
         assert np.array_equal(got, want), (kernels, np.argwhere(got != want)[:4])
     finally:
         ctx.set_variant("auto")
+
+
+# ------------------------------------------------------------------ rgb2bayer
+@pytest.mark.parametrize("w,h", [(9, 7), (16, 4), (130, 21), (1030, 9), (1024, 16), (3840, 6)])
+def test_rgb2bayer_all_patterns(ctx, orc, rng, w, h):
+    """gstrgb2bayer.c:254-267 (byte 3 / 1 / 2 of the ARGB pixel by row/column parity). Widths that are not a
+    multiple of the 16 pixels a lane owns, rows that start off 16-byte alignment (w = 9: mosaic pitch 12),
+    a 4K row, and a source pitch with padding."""
+    for pad in (0, 12):
+        src = frames.random_u8(rng, h, 4 * w + pad)
+        mstride = frames.round_up_4(w)
+        for fmt in BAYER_FORMATS:
+            want = orc.rgb2bayer(src, w, h, fmt)
+            d_src = ctx.upload(src)
+            d_dst = ctx.alloc(h * mstride)
+            ctx.rgb2bayer(d_src, src.shape[1], d_dst, mstride, w, h, BAYER_FORMATS[fmt])
+            got = ctx.download(d_dst, h * mstride).reshape(h, mstride)
+            assert np.array_equal(got[:, :w], want[:, :w]), (w, h, pad, fmt, np.argwhere(got[:, :w] != want[:, :w])[:4])
+
+
+def test_rgb2bayer_batch_then_bayer2rgb_round_trip(ctx, orc, rng):
+    """a batch of frames through rgb2bayer, and the size-independent property the plugin pair offers: mosaicing
+    a demosaiced frame returns the original samples (each pixel keeps its own colour sample)"""
+    w, h, n = 256, 48, 3
+    mosaic = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    d_m = ctx.upload(mosaic)
+    d_rgb = ctx.alloc(n * h * w * 4)
+    ctx.bayer2rgb(d_m, w, d_rgb, 4 * w, w, h, BAYER_FORMATS["bggr"], RGB_OFFSETS["ARGB"], nframes=n)
+    d_back = ctx.alloc(n * h * w)
+    ctx.rgb2bayer(d_rgb, 4 * w, d_back, w, w, h, BAYER_FORMATS["bggr"], nframes=n)
+    back = ctx.download(d_back, n * h * w).reshape(n, h, w)
+    rgb = ctx.download(d_rgb, n * h * w * 4).reshape(n, h, 4 * w)
+    for i in range(n):
+        assert np.array_equal(back[i], orc.rgb2bayer(rgb[i], w, h, "bggr")[:, :w]), i
+    assert np.array_equal(back, mosaic)
