@@ -171,8 +171,10 @@ int b200vf_dilate (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, int wi
  * AYUV), other bytes copied. exact != 0: separate fp32 multiply and
  * add in the reference's tap order (bit-exact); exact == 0: fused multiply-add
  * (faster, within 1 LSB of the u8 output). Row-shard arguments: the frame is
- * rows [row0,row0+rows) of full_height; halo rows (center above/below) must be
- * present around d_src unless at the global edge. */
+ * rows [row0,row0+rows) of full_height; halo rows (center above/below; center+1
+ * when p0 > 0 and stride == 4*width, because a pixel's last p0 bytes are the
+ * first bytes of the next row) must be present around d_src unless at the
+ * global edge. */
 int b200vf_gauss_kernel (float sigma, float *kernel, float *kernel_sum, int capacity);
 int b200vf_gaussblur (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, int width, int full_height,
     int row0, int rows, int stride, size_t frame_stride, int nframes, int p0,

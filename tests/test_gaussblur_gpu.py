@@ -148,6 +148,28 @@ def test_row_sharded_equals_whole(ctx, vf, orc, rng):
     assert np.array_equal(got, want), np.argwhere(got != want)[:6]
 
 
+@pytest.mark.parametrize("p0", [0, 1, 2, 3])
+def test_row_shards_many_cuts_equal_whole(ctx, vf, p0):
+    """every shard boundary reproduces the whole-frame bytes, including the channels of a row's last pixel that
+    live in the next row (p0 > 0, unpadded rows): 4 seeds x 5 cuts, sigma 5 and 1.2; shards see center+1 halo rows"""
+    w, h = 64, 120
+    d_dst = ctx.alloc(h * 4 * w)
+    d_ref = ctx.alloc(h * 4 * w)
+    for seed in range(4):
+        fr = frames.random_u8(np.random.default_rng(100 + seed), h, 4 * w)
+        d_src = ctx.upload(fr)
+        for sigma in (5, 1.2):
+            k, ks = vf.gauss_kernel(sigma)
+            ctx.gaussblur(d_src, d_ref, w, h, 4 * w, p0, k, ks)
+            want = ctx.download(d_ref, fr.size)
+            for cut in (16, 40, 61, 64, 100):
+                for (row0, rows) in [(0, cut), (cut, h - cut)]:
+                    ctx.gaussblur(d_src.ptr + row0 * 4 * w, d_dst.ptr + row0 * 4 * w, w, rows, 4 * w, p0, k, ks,
+                                  row0=row0, rows=rows, full_height=h)
+                got = ctx.download(d_dst, fr.size)
+                assert np.array_equal(got, want), (seed, sigma, cut, np.argwhere(got.reshape(h, -1) != want.reshape(h, -1))[:6])
+
+
 def test_4k_sigma5_band_exact(ctx, vf, orc, rng):
     """BASELINE.json configs[2] geometry: 3840x2160, sigma=5. The CPU oracle needs ~1.7 s/frame at 4K,
     so compare a 256-row band that contains the top edge exactly, plus a size-independent property
