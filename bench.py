@@ -444,7 +444,7 @@ def side_measurements(ctx, torch, b200vf, st, side, peak):
             d_idx = torch.from_numpy(idx).cuda()
             t = timeit(lambda: ctx.remap(a, b, d_idx, w, h, 4, 4 * w, nframes=n4, stream=st))
             rec("fisheye_8k_remap", n4, px, 8, t, {"host_map_build_s": t_map, "index_table_bytes_per_px": 4})
-            # the same table step-coded (b200vf_gt_pack_index): what the fisheye element runs on 4-byte formats
+            # the same table step-coded (b200vf_gt_pack_index, optional API: 1.5 B/px of table instead of 4)
             t0 = time.perf_counter()
             packed, raw_groups = b200vf.gt_pack_index(idx, w, h)
             t_pack = time.perf_counter() - t0

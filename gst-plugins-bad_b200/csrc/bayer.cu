@@ -138,19 +138,17 @@ int launch_direct (b200vf_ctx *ctx, const BayerParams &p, const BayerEpilogue &e
 }
 
 template <int ORDER>
-cudaError_t set_smem_order () {
-  cudaError_t e;
-  if ((e = cudaFuncSetAttribute (bayer2rgb_direct_kernel<ORDER, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES))) return e;
-  if ((e = cudaFuncSetAttribute (bayer2rgb_direct_kernel<ORDER, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES))) return e;
-  if ((e = cudaFuncSetAttribute (bayer2rgb_direct_kernel<ORDER, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES))) return e;
-  return cudaFuncSetAttribute (bayer2rgb_direct_kernel<ORDER, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES);
+int set_smem_order (b200vf_ctx *ctx) {
+  int rc;
+  if ((rc = b200vf_func_smem (ctx, (const void *) bayer2rgb_direct_kernel<ORDER, true, 1>, LUT_SMEM_BYTES))) return rc;
+  if ((rc = b200vf_func_smem (ctx, (const void *) bayer2rgb_direct_kernel<ORDER, false, 1>, LUT_SMEM_BYTES))) return rc;
+  if ((rc = b200vf_func_smem (ctx, (const void *) bayer2rgb_direct_kernel<ORDER, true, 2>, LUT_SMEM_BYTES))) return rc;
+  return b200vf_func_smem (ctx, (const void *) bayer2rgb_direct_kernel<ORDER, false, 2>, LUT_SMEM_BYTES);
 }
-int bayer_direct_set_smem () {
-  B200VF_CHECK_CUDA (set_smem_order<0> ());
-  B200VF_CHECK_CUDA (set_smem_order<1> ());
-  B200VF_CHECK_CUDA (set_smem_order<2> ());
-  B200VF_CHECK_CUDA (set_smem_order<3> ());
-  return B200VF_OK;
+int bayer_direct_set_smem (b200vf_ctx *ctx) {
+  int rc;
+  if ((rc = set_smem_order<0> (ctx)) || (rc = set_smem_order<1> (ctx)) || (rc = set_smem_order<2> (ctx))) return rc;
+  return set_smem_order<3> (ctx);
 }
 
 }  // namespace
@@ -186,11 +184,9 @@ static int bayer_common (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, 
   cudaStream_t s = b200vf_stream (ctx, stream);
   BayerEpilogue epi;              // 1 KB table: built per call, passed by value to the kernel
   bayer_build_epilogue (epi, out_r, out_g, out_b, luma_table768, lut);
-  static bool attr_set = false;
-  if (epi.mode && !attr_set) {
-    int rc = bayer_direct_set_smem ();
+  if (epi.mode) {
+    int rc = bayer_direct_set_smem (ctx);
     if (rc) return rc;
-    attr_set = true;
   }
 
   if (allow_tma && ctx->variant != 1 &&

@@ -251,12 +251,8 @@ namespace {
 
 template <int ORDER, int MODE>
 int launch_tma_mode (b200vf_ctx *ctx, const CUtensorMap &map, const TmaParams &p, const BayerEpilogue &epi, cudaStream_t s) {
-  static bool attr_set = false;
   const int smem = STAGES * STAGE_BYTES + (MODE ? LUT_SMEM_BYTES : 0);
-  if (!attr_set) {
-    B200VF_CHECK_CUDA (cudaFuncSetAttribute (bayer2rgb_tma_kernel<ORDER, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  if (int rc = b200vf_func_smem (ctx, (const void *) bayer2rgb_tma_kernel<ORDER, MODE>, smem)) return rc;
   int ntiles = p.tiles_x * p.tiles_y * p.nframes;
   int per_sm = 2;                              // CTAs per SM (measured sweep 1..6 in profiles/: 2 is best; more CTAs only add DRAM page conflicts)
   if (const char *e = getenv ("B200VF_TMA_CTAS_PER_SM")) { int v = atoi (e); if (v >= 1 && v <= 8) per_sm = v; }   // tuning knob

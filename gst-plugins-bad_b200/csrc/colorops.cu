@@ -460,8 +460,7 @@ B200VF_API int b200vf_exclusion (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t 
   }
   p.magic = factor >= 2 ? (uint32_t) (0x100000000ull / (uint64_t) factor) + 1u : 0u;
   p.factor = factor;
-  static bool attr = false;
-  if (!attr) { B200VF_CHECK_CUDA (cudaFuncSetAttribute (exclusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAB_SMEM)); attr = true; }
+  if (int rc = b200vf_func_smem (ctx, (const void *) exclusion_kernel, TAB_SMEM)) return rc;
   size_t n16 = npix_total / 4;
   int ntail = (int) (npix_total - n16 * 4);
   if (stream_enabled (ctx) && n16 >= 1024) {
@@ -539,13 +538,11 @@ B200VF_API int b200vf_coloreffects_rgb (b200vf_ctx *ctx, uint8_t *d_data, int wi
   B200VF_REQUIRE (off_r >= 0 && off_r <= mo && off_g >= 0 && off_g <= mo && off_b >= 0 && off_b <= mo &&
       off_r != off_g && off_g != off_b && off_r != off_b, B200VF_E_INVAL, "coloreffects: offsets");
   cudaStream_t s = b200vf_stream (ctx, stream);
-  static bool attr = false;
-  if (!attr) {
-    B200VF_CHECK_CUDA (cudaFuncSetAttribute (coloreffects4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAB_SMEM));
-    B200VF_CHECK_CUDA (cudaFuncSetAttribute (coloreffects4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAB_SMEM));
-    B200VF_CHECK_CUDA (cudaFuncSetAttribute (coloreffects3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAB_SMEM));
-    B200VF_CHECK_CUDA (cudaFuncSetAttribute (chromahold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAB_SMEM));
-    attr = true;
+  {
+    int rc;
+    if ((rc = b200vf_func_smem (ctx, (const void *) coloreffects4_kernel<false>, TAB_SMEM)) ||
+        (rc = b200vf_func_smem (ctx, (const void *) coloreffects4_kernel<true>, TAB_SMEM)) ||
+        (rc = b200vf_func_smem (ctx, (const void *) coloreffects3_kernel, TAB_SMEM))) return rc;
   }
   if (pixel_stride == 4) {
     B200VF_REQUIRE (((uintptr_t) d_data) % 4 == 0 && row_stride % 4 == 0 && frame_stride % 4 == 0, B200VF_E_INVAL,
@@ -586,11 +583,7 @@ B200VF_API int b200vf_coloreffects_ayuv (b200vf_ctx *ctx, uint8_t *d_data, int w
       B200VF_E_INVAL, "coloreffects_ayuv: stride / alignment");
   B200VF_REQUIRE (off_y >= 0 && off_y <= 3 && off_u >= 0 && off_u <= 3 && off_v >= 0 && off_v <= 3 &&
       off_y != off_u && off_u != off_v && off_y != off_v, B200VF_E_INVAL, "coloreffects_ayuv: offsets");
-  static bool attr = false;
-  if (!attr) {
-    B200VF_CHECK_CUDA (cudaFuncSetAttribute (coloreffects4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAB_SMEM));
-    attr = true;
-  }
+  if (int rc = b200vf_func_smem (ctx, (const void *) coloreffects4_kernel<true>, TAB_SMEM)) return rc;
   ColorParams p;
   p.sr = shift_of (off_y); p.sg = shift_of (off_u); p.sb = shift_of (off_v);
   p.keep_mask = ~((0xffu << p.sr) | (0xffu << p.sg) | (0xffu << p.sb));
@@ -620,11 +613,7 @@ B200VF_API int b200vf_chromahold (b200vf_ctx *ctx, uint8_t *d_data, int width, i
       off_r != off_g && off_g != off_b && off_r != off_b, B200VF_E_INVAL, "chromahold: offsets");
   B200VF_REQUIRE (target_r >= 0 && target_r <= 255 && target_g >= 0 && target_g <= 255 && target_b >= 0 && target_b <= 255 &&
       tolerance >= 0 && tolerance <= 180, B200VF_E_PROPERTY, "chromahold: target/tolerance out of range");
-  static bool attr = false;
-  if (!attr) {
-    B200VF_CHECK_CUDA (cudaFuncSetAttribute (chromahold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAB_SMEM));
-    attr = true;
-  }
+  if (int rc = b200vf_func_smem (ctx, (const void *) chromahold_kernel, TAB_SMEM)) return rc;
   ChromaParams p;
   p.sr = shift_of (off_r); p.sg = shift_of (off_g); p.sb = shift_of (off_b);
   p.keep_mask = ~((0xffu << p.sr) | (0xffu << p.sg) | (0xffu << p.sb));

@@ -45,9 +45,17 @@ void b200vf_set_error (const char *fmt, ...);
     }                                                                                \
   } while (0)
 
+// Every op starts here: the calling thread may be any streaming thread (a GStreamer pad task, a Python worker), whose
+// current CUDA device is whatever it last used. Launches, attributes and allocations below belong to the context's
+// device, so it is made current for the calling thread (left that way, as CUDA libraries do).
 static inline cudaStream_t b200vf_stream (b200vf_ctx *ctx, void *stream) {
+  cudaSetDevice (ctx->device);
   return stream ? (cudaStream_t) stream : ctx->stream;
 }
+
+// Opt-in to `bytes` of dynamic shared memory for kernel `fn`, once per (kernel, device): the attribute lives in the
+// device's context, and ops are called from several threads (core.cu; thread-safe). Returns a b200vf status.
+int b200vf_func_smem (b200vf_ctx *ctx, const void *fn, int bytes);
 
 // Every kernel launch goes through this so that gpu_launches is a count, not a guess.
 static inline int b200vf_launched (b200vf_ctx *ctx, const char *name) {

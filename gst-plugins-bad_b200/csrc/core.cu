@@ -270,3 +270,20 @@ int b200vf_next_tile_counter (b200vf_ctx *ctx, cudaStream_t s, unsigned int **ou
   *out = c;
   return B200VF_OK;
 }
+
+// ---------------------------------------------------------------- per-device kernel attributes
+#include <mutex>
+#include <set>
+#include <utility>
+int b200vf_func_smem (b200vf_ctx *ctx, const void *fn, int bytes)
+{
+  static std::mutex mu;
+  static std::set<std::pair<const void *, int>> done;      // (kernel, device) pairs already opted in
+  std::lock_guard<std::mutex> lock (mu);
+  const std::pair<const void *, int> key (fn, ctx->device);
+  if (done.count (key)) return B200VF_OK;
+  B200VF_CHECK_CUDA (cudaSetDevice (ctx->device));
+  B200VF_CHECK_CUDA (cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert (key);
+  return B200VF_OK;
+}

@@ -129,11 +129,10 @@ int b200vf_dilate_tma (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, in
   p.tiles_x = (width + TW - 1) / TW;
   p.tiles_y = (rows_out + TH - 1) / TH;
   const int smem = STAGES * STAGE_BYTES;
-  static bool attr = false;
-  if (!attr) {
-    B200VF_CHECK_CUDA (cudaFuncSetAttribute (dilate_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    B200VF_CHECK_CUDA (cudaFuncSetAttribute (dilate_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
+  {
+    int rc;
+    if ((rc = b200vf_func_smem (ctx, (const void *) dilate_tma_kernel<true>, smem)) ||
+        (rc = b200vf_func_smem (ctx, (const void *) dilate_tma_kernel<false>, smem))) return rc;
   }
   const int ntiles = p.tiles_x * p.tiles_y * nframes;
   int per_sm = 2;                             // as for bayer2rgb_tma: more CTAs only add DRAM page conflicts

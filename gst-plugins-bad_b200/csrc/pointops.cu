@@ -75,12 +75,8 @@ B200VF_API int b200vf_lut4 (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_ds
   if (head > npix_total) head = npix_total;
   bool aligned = (((uintptr_t) (d_src + 4 * head)) % 16 == 0) && (((uintptr_t) (d_dst + 4 * head)) % 16 == 0);
   cudaStream_t s = b200vf_stream (ctx, stream);
-  static bool attr_set = false;
   const int smem = 256 * 32 * 4;
-  if (!attr_set) {
-    B200VF_CHECK_CUDA (cudaFuncSetAttribute (lut4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  if (int rc = b200vf_func_smem (ctx, (const void *) lut4_kernel, smem)) return rc;
   size_t body = aligned ? (npix_total - head) / 4 : 0;          // 128-bit groups
   size_t done = head + body * 4;
   // scalar leftovers: head pixels + tail pixels (<= 3 each), or everything when misaligned

@@ -101,11 +101,10 @@ static inline bool stream_enabled (const b200vf_ctx *ctx) { return ctx->variant 
 template <class OP>
 int stream_launch (b200vf_ctx *ctx, const uint8_t *src, uint8_t *dst, size_t nbytes, const OP &op, cudaStream_t s, const char *name,
     int consumers = 8) {
-  static bool attr = false;
-  if (!attr) {
-    B200VF_CHECK_CUDA (cudaFuncSetAttribute (stream_kernel<OP, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-    B200VF_CHECK_CUDA (cudaFuncSetAttribute (stream_kernel<OP, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-    attr = true;
+  {
+    int rc0;
+    if ((rc0 = b200vf_func_smem (ctx, (const void *) stream_kernel<OP, 8>, ST_SMEM)) ||
+        (rc0 = b200vf_func_smem (ctx, (const void *) stream_kernel<OP, 16>, ST_SMEM))) return rc0;
   }
   if (const char *e = getenv ("B200VF_STREAM_CONSUMERS")) { int v = atoi (e); if (v == 8 || v == 16) consumers = v; }   // tuning knob
   const size_t nchunks = (nbytes + ST_CHUNK - 1) / ST_CHUNK;
