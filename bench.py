@@ -33,6 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "gst-plugins-bad_b200"))
 W4K, H4K = 3840, 2160
 METRIC = "bayer2rgb frames/s (3840x2160 bggr->RGBA)"
 FALLBACK_HBM_GBS = 6650.0
+_json_out = sys.stdout
 # dram__bytes_read.sum + dram__bytes_write.sum of bayer2rgb_tma per 4K frame, from the committed ncu capture
 # profiles/r01_bayer2rgb_tma_final.md (938.2 MB for a 24-frame launch; algorithmic 41.47 MB/frame)
 NCU_TRAFFIC_BYTES_PER_FRAME = 938.21056e6 / 24
@@ -115,7 +116,7 @@ def run_reference_arm(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_json_out, flush=True)
     return 0
 
 
@@ -173,6 +174,12 @@ def main():
     ap.add_argument("--profile", action="store_true",
                     help="only the timed hot-path steps (for runs under ncu: numbers printed there are not bench values)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: native libraries print there too (NCCL's "NCCL version ..." banner
+    # under NCCL_DEBUG=VERSION), so file descriptor 1 is pointed at stderr and the line goes to a private duplicate.
+    global _json_out
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -271,7 +278,8 @@ def main():
 
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "frames_per_step": nfr, "kernel": ctx.last_kernel()}))
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "frames_per_step": nfr, "kernel": ctx.last_kernel()}),
+                  file=_json_out, flush=True)
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -340,7 +348,7 @@ def main():
                 line["elements"] = side_measurements(ctx, torch, b200vf, st, side, peak)
             except Exception as ex:                                    # side numbers must never sink the headline
                 line["elements"] = {"error": str(ex)}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
