@@ -403,6 +403,18 @@ def side_measurements(ctx, torch, b200vf, st, side, peak):
                 ctx.lut4(dst, dst, n * px, sol, stream=st)
             t = timeit(unfused)
             rec("chain_8k_unfused", n, px, 21, t, {"launches_per_frame_batch": 3})
+        # videofiltersbad plugin on the same planes taken as luma: zebrastripe (in place, 2 B of
+        # traffic per sample), videodiff's luma loop (3 B), scenechange's SAD (2 B, read only)
+        src2 = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, device="cuda")
+        lum_out = torch.empty_like(src2)
+        sums = torch.zeros(n, dtype=torch.int32, device="cuda")
+        t = timeit(lambda: ctx.sad_u8(src, src2, w, w, h, sums, nframes=n, stream=st))
+        rec("scenechange_sad_%s" % tag, n, px, 2, t)
+        t = timeit(lambda: ctx.videodiff_luma(src, src2, lum_out, w, w, h, nframes=n, stream=st))
+        rec("videodiff_luma_%s" % tag, n, px, 3, t)
+        t = timeit(lambda: ctx.zebrastripe(src2, 1, w, w, h, threshold=90, nframes=n, stream=st))
+        rec("zebrastripe_%s" % tag, n, px, 2, t)
+        del src2, lum_out, sums
         del src
         # 4-byte -> 4-byte elements on the RGBA batch
         n4 = max(2, min(n, int(3e9 // (px * 8))))

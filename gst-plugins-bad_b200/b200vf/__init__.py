@@ -85,6 +85,12 @@ _SIGS = {
     "b200vf_gt_pack_index": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz)]),
     "b200vf_gt_unpack_index": (_i, [_vp, _sz, _i, _i, _vp]),
     "b200vf_remap_packed": (_i, [_vp, _vp, _vp, _vp, _i, _i, _sz, _i, _u32, _vp]),
+    "b200vf_zebrastripe_y_threshold": (_i, [_i]),
+    "b200vf_zebrastripe": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _i, _i, _i, _vp]),
+    "b200vf_videodiff_luma": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _vp]),
+    "b200vf_sad_u8": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _vp, _vp]),
+    "b200vf_scenechange_reset": (_i, [_vp]),
+    "b200vf_scenechange_update": (_i, [_vp, C.c_double, C.POINTER(_i)]),
     "b200vf_bayer2rgb_fused": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b200vf_comm_unique_id": (_i, [_vp]),
     "b200vf_comm_create": (_i, [_vp, _vp, _i, _i, C.POINTER(_vp)]),
@@ -274,6 +280,22 @@ class Context:
         bad = C.c_ulonglong(0)
         check(lib.b200vf_gauss_selftest_div(self.h, float(divisor), int(lo_bits), int(hi_bits), C.byref(bad)))
         return bad.value
+
+    # ---- videofiltersbad plugin
+    def zebrastripe(self, luma, pixel_stride, row_stride, width, height, threshold=90, t=0, nframes=1, frame_stride=None,
+                    stream=None):
+        fs = frame_stride if frame_stride is not None else row_stride * height
+        check(lib.b200vf_zebrastripe(self.h, _ptr(luma), pixel_stride, row_stride, fs, nframes, width, height,
+                                     lib.b200vf_zebrastripe_y_threshold(threshold), t, stream))
+
+    def videodiff_luma(self, old, new, out, stride, width, height, threshold=10, t=0, nframes=1, frame_stride=None, stream=None):
+        fs = frame_stride if frame_stride is not None else stride * height
+        check(lib.b200vf_videodiff_luma(self.h, _ptr(old), stride, fs, _ptr(new), stride, fs, _ptr(out), stride, fs,
+                                        width, height, nframes, threshold, t, stream))
+
+    def sad_u8(self, a, b, stride, width, height, sums, nframes=1, frame_stride=None, stream=None):
+        fs = frame_stride if frame_stride is not None else stride * height
+        check(lib.b200vf_sad_u8(self.h, _ptr(a), stride, fs, _ptr(b), stride, fs, width, height, nframes, _ptr(sums), stream))
 
     def gauss_selftest_finish(self, lo_bits=0, hi_bits=0xffffffff):
         """mismatches between the blur's fp32-only final rounding and (guint8) CLAMP (q + 0.5 [fp64], 0, 255)"""
@@ -536,3 +558,19 @@ class Element:
 
     def transform_device(self, d_in, d_out, nframes=1, stream=None):
         check(lib.b200vf_element_transform_device(self.h, _ptr(d_in), _ptr(d_out), nframes, stream))
+
+
+class SceneChange:
+    """the scenechange element's decision state (gstscenechange.c:196-236) on the library's host code"""
+
+    class _State(C.Structure):
+        _fields_ = [("diffs", C.c_double * 5), ("n_diffs", C.c_int)]
+
+    def __init__(self):
+        self.st = self._State()
+        check(lib.b200vf_scenechange_reset(C.byref(self.st)))
+
+    def update(self, score):
+        ch = C.c_int(0)
+        check(lib.b200vf_scenechange_update(C.byref(self.st), float(score), C.byref(ch)))
+        return bool(ch.value)

@@ -21,7 +21,7 @@ struct b200vf_ctx {
   int variant = 0;                 // 0 auto, 1 direct, 2 tma
   void *tma_encode = nullptr;      // cuTensorMapEncodeTiled entry point (driver API via cudart)
   unsigned int *tile_counters = nullptr;   // ring of work counters for dynamically scheduled kernels
-  unsigned int tile_counter_next = 0;
+  std::atomic<unsigned int> tile_counter_next{0};   // ops run on several threads
   cudaMemPool_t scratch_pool = nullptr;    // stream-ordered scratch (gaussblur pre-pass ...): never trimmed at synchronisation points
 };
 

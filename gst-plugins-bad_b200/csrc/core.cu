@@ -7,6 +7,7 @@
 #include <vector>
 
 static thread_local char g_err[512] = "";
+static const unsigned kTileCounterRing = 256;
 
 void b200vf_set_error (const char *fmt, ...) {
   va_list ap;
@@ -86,6 +87,14 @@ B200VF_API int b200vf_ctx_create (int device, b200vf_ctx **out) {
       delete c;
       return B200VF_E_CUDA;
     }
+  }
+  e = cudaMalloc ((void **) &c->tile_counters, kTileCounterRing * sizeof (unsigned int));
+  if (e != cudaSuccess) {
+    b200vf_set_error ("cudaMalloc (tile counters): %s", cudaGetErrorString (e));
+    cudaMemPoolDestroy (c->scratch_pool);
+    cudaStreamDestroy (c->stream);
+    delete c;
+    return B200VF_E_NOMEM;
   }
   *out = c;
   return B200VF_OK;
@@ -257,15 +266,11 @@ B200VF_API int b200vf_pool_download (b200vf_pool *pool, int i, void *host_dst, s
   return B200VF_OK;
 }
 
-// Work counters for dynamically scheduled persistent kernels: a ring of 256 counters, each zeroed
+// Work counters for dynamically scheduled persistent kernels: a ring of 256 counters (allocated with the context), each zeroed
 // on the launching stream right before its launch (stream-ordered, so launches on the same stream
 // never share a live counter; 256 in-flight launches across streams would be needed to collide).
 int b200vf_next_tile_counter (b200vf_ctx *ctx, cudaStream_t s, unsigned int **out) {
-  const unsigned ring = 256;
-  if (!ctx->tile_counters) {
-    B200VF_CHECK_CUDA (cudaMalloc ((void **) &ctx->tile_counters, ring * sizeof (unsigned int)));
-  }
-  unsigned int *c = ctx->tile_counters + (ctx->tile_counter_next++ % ring);
+  unsigned int *c = ctx->tile_counters + (ctx->tile_counter_next.fetch_add (1, std::memory_order_relaxed) % kTileCounterRing);
   B200VF_CHECK_CUDA (cudaMemsetAsync (c, 0, sizeof (unsigned int), s));
   *out = c;
   return B200VF_OK;

@@ -1,0 +1,341 @@
+// videofilters.cu - the `videofiltersbad` plugin's per-pixel loops for sm_100a (the sibling
+// filters with the same GstVideoFilter boundary, on planar / packed YUV instead of packed RGB).
+//
+//   zebrastripe  gst_zebra_stripe_transform_frame_ip     gst/videofilters/gstzebrastripe.c:205-253
+//   videodiff    gst_video_diff_transform_frame_ip_planarY gst/videofilters/gstvideodiff.c:94-129 (luma plane; the
+//                chroma planes are plain copies)
+//   scenechange  get_frame_score -> orc_sad_nxm_u8       gst/videofilters/gstscenechange.c:141-155,
+//                gstscenechangeorc.orc (`accsadubl`), C backup gstscenechangeorc-dist.c:147-180;
+//                the decision that follows (:196-236) is host arithmetic on five doubles (b200vf_scenechange_update).
+//
+// All three are byte streams bound by HBM: 2 (zebrastripe, in place), 3 (videodiff) and 2 (SAD, read only) bytes of
+// traffic per luma sample. A thread owns the same 16-byte column of four consecutive rows, so four independent
+// 128-bit loads per source are in flight before the first byte is used; the per-byte tests are done four bytes per
+// instruction with the SIMD-in-word video instructions (vcmpgeu4 / vabsdiffu4 / vsadu4). Rows whose base or pitch
+// is not 16-byte aligned take the same code on 32-bit words; the last width % 4 samples of a row are done bytewise.
+#include "common.cuh"
+
+namespace {
+
+constexpr int VF_ROWS = 4;                  // rows per thread
+constexpr int VF_TX = 64, VF_TY = 4;        // threads per CTA: 64 columns x 4 row groups
+
+// 0xff in every byte lane whose pixel index i (lane b of the word holds pixel i0 + b) has (i + c) & 4 set
+__device__ __forceinline__ uint32_t stripe_mask4 (int i0, int c) {
+  const uint32_t s = (uint32_t) (i0 + c);
+  const uint32_t base = (s & 4u) ? 0xffffffffu : 0u;
+  const uint32_t k = s & 3u;                                 // lanes b >= 4 - k carry into bit 2
+  const uint32_t flip = k ? (0xffffffffu << (8u * (4u - k))) : 0u;
+  return base ^ flip;
+}
+
+// ---- zebrastripe --------------------------------------------------------------------------------------
+// planar luma (pixel_stride 1): word = 4 consecutive pixels
+__device__ __forceinline__ uint32_t zebra_word (uint32_t v, uint32_t thr4, int i0, int c) {
+  const uint32_t m = __vcmpgeu4 (v, thr4) & stripe_mask4 (i0, c);
+  return (v & ~m) | (0x10101010u & m);
+}
+__device__ __forceinline__ uint8_t zebra_byte (uint8_t v, int thr, int i, int c) {
+  return (v >= thr && ((i + c) & 4)) ? (uint8_t) 16 : v;
+}
+
+template <int WORDS>   // words per thread per row: 4 (128-bit accesses) or 1
+__global__ void __launch_bounds__ (VF_TX * VF_TY)
+zebra_planar_kernel (uint8_t *luma, int row_stride, size_t frame_stride, int width, int height, int thr, int t)
+{
+  const int w0 = (blockIdx.x * VF_TX + threadIdx.x) * WORDS;           // first word of this thread's column
+  const int j0 = (blockIdx.y * VF_TY + threadIdx.y) * VF_ROWS;
+  const int nwords = width >> 2;
+  uint8_t *base = luma + (size_t) blockIdx.z * frame_stride;
+  const int tt = t + blockIdx.z;                                       // the element counts t up once per frame (:217)
+  const uint32_t thr4 = (uint32_t) min (thr, 255) * 0x01010101u;
+  const bool none = thr > 255;                                         // y_threshold <= 235 for threshold <= 100; kept for any input
+  if (w0 < nwords && !none) {
+    uint32_t v[VF_ROWS][WORDS];
+#pragma unroll
+    for (int r = 0; r < VF_ROWS; r++) {
+      if (j0 + r >= height) break;
+      const uint32_t *p = reinterpret_cast<const uint32_t *> (base + (size_t) (j0 + r) * row_stride) + w0;
+      if (WORDS == 4 && w0 + 4 <= nwords) { const uint4 q = *reinterpret_cast<const uint4 *> (p); v[r][0] = q.x; v[r][1] = q.y; v[r][2] = q.z; v[r][3] = q.w; }
+      else
+#pragma unroll
+        for (int k = 0; k < WORDS; k++) if (w0 + k < nwords) v[r][k] = p[k];
+    }
+#pragma unroll
+    for (int r = 0; r < VF_ROWS; r++) {
+      if (j0 + r >= height) break;
+      uint32_t *p = reinterpret_cast<uint32_t *> (base + (size_t) (j0 + r) * row_stride) + w0;
+      uint32_t o[WORDS];
+#pragma unroll
+      for (int k = 0; k < WORDS; k++) o[k] = zebra_word (v[r][k], thr4, 4 * (w0 + k), j0 + r + tt);
+      if (WORDS == 4 && w0 + 4 <= nwords) *reinterpret_cast<uint4 *> (p) = make_uint4 (o[0], o[1], o[2], o[3]);
+      else
+#pragma unroll
+        for (int k = 0; k < WORDS; k++) if (w0 + k < nwords) p[k] = o[k];
+    }
+  }
+  // the last width % 4 samples of each row
+  if (blockIdx.x == 0 && threadIdx.x < (width & 3) && !none) {
+    const int i = (nwords << 2) + threadIdx.x;
+    for (int r = 0; r < VF_ROWS; r++) {
+      if (j0 + r >= height) break;
+      uint8_t *p = base + (size_t) (j0 + r) * row_stride + i;
+      *p = zebra_byte (*p, thr, i, j0 + r + tt);
+    }
+  }
+}
+
+// packed formats: the luma sample of pixel i is byte i * ps of the row that starts at `luma` (ps = 2: YUY2 / UYVY,
+// ps = 4: AYUV). One pixel per thread and row; the other bytes are not touched (bytewise read-modify-write).
+__global__ void __launch_bounds__ (VF_TX * VF_TY)
+zebra_packed_kernel (uint8_t *luma, int ps, int row_stride, size_t frame_stride, int width, int height, int thr, int t)
+{
+  const int i = blockIdx.x * VF_TX + threadIdx.x;
+  const int j0 = (blockIdx.y * VF_TY + threadIdx.y) * VF_ROWS;
+  if (i >= width) return;
+  uint8_t *base = luma + (size_t) blockIdx.z * frame_stride + (size_t) i * ps;
+  const int tt = t + blockIdx.z;
+  uint8_t v[VF_ROWS];
+#pragma unroll
+  for (int r = 0; r < VF_ROWS; r++) if (j0 + r < height) v[r] = base[(size_t) (j0 + r) * row_stride];
+#pragma unroll
+  for (int r = 0; r < VF_ROWS; r++)
+    if (j0 + r < height && v[r] >= thr && ((i + j0 + r + tt) & 4)) base[(size_t) (j0 + r) * row_stride] = 16;
+}
+
+// ---- videodiff ----------------------------------------------------------------------------------------
+// (s2 < s1 - threshold) || (s2 > s1 + threshold) in int arithmetic == |s2 - s1| > threshold
+__device__ __forceinline__ uint32_t diff_word (uint32_t s1, uint32_t s2, uint32_t thr4, bool none, int i0, int c) {
+  const uint32_t m = none ? 0u : __vcmpgtu4 (__vabsdiffu4 (s1, s2), thr4);
+  const uint32_t mark = (0x10101010u & stripe_mask4 (i0, c)) | (0xf0f0f0f0u & ~stripe_mask4 (i0, c));     // 16 on the stripe, else 240
+  return (s2 & ~m) | (mark & m);
+}
+
+template <int WORDS>
+__global__ void __launch_bounds__ (VF_TX * VF_TY)
+videodiff_kernel (const uint8_t *s_old, int old_stride, size_t old_fs, const uint8_t *s_new, int new_stride, size_t new_fs,
+    uint8_t *dst, int dst_stride, size_t dst_fs, int width, int height, int threshold, int t)
+{
+  const int w0 = (blockIdx.x * VF_TX + threadIdx.x) * WORDS;
+  const int j0 = (blockIdx.y * VF_TY + threadIdx.y) * VF_ROWS;
+  const int nwords = width >> 2;
+  const uint8_t *a = s_old + (size_t) blockIdx.z * old_fs, *b = s_new + (size_t) blockIdx.z * new_fs;
+  uint8_t *d = dst + (size_t) blockIdx.z * dst_fs;
+  const bool none = threshold >= 255;                       // no byte difference exceeds 255
+  const uint32_t thr4 = (uint32_t) max (0, min (threshold, 255)) * 0x01010101u;
+  const bool all = threshold < 0;                           // every sample differs by more than a negative threshold
+  if (w0 < nwords) {
+    uint32_t va[VF_ROWS][WORDS], vb[VF_ROWS][WORDS];
+#pragma unroll
+    for (int r = 0; r < VF_ROWS; r++) {
+      if (j0 + r >= height) break;
+      const uint32_t *pa = reinterpret_cast<const uint32_t *> (a + (size_t) (j0 + r) * old_stride) + w0;
+      const uint32_t *pb = reinterpret_cast<const uint32_t *> (b + (size_t) (j0 + r) * new_stride) + w0;
+      if (WORDS == 4 && w0 + 4 <= nwords) {
+        const uint4 qa = ld_stream_v4 (pa), qb = ld_stream_v4 (pb);
+        va[r][0] = qa.x; va[r][1] = qa.y; va[r][2] = qa.z; va[r][3] = qa.w;
+        vb[r][0] = qb.x; vb[r][1] = qb.y; vb[r][2] = qb.z; vb[r][3] = qb.w;
+      } else
+#pragma unroll
+        for (int k = 0; k < WORDS; k++) if (w0 + k < nwords) { va[r][k] = ldg_u32 (pa + k); vb[r][k] = ldg_u32 (pb + k); }
+    }
+#pragma unroll
+    for (int r = 0; r < VF_ROWS; r++) {
+      if (j0 + r >= height) break;
+      uint32_t *pd = reinterpret_cast<uint32_t *> (d + (size_t) (j0 + r) * dst_stride) + w0;
+      uint32_t o[WORDS];
+#pragma unroll
+      for (int k = 0; k < WORDS; k++) {
+        const int i0 = 4 * (w0 + k), c = j0 + r + t;
+        o[k] = all ? ((0x10101010u & stripe_mask4 (i0, c)) | (0xf0f0f0f0u & ~stripe_mask4 (i0, c)))
+                   : diff_word (va[r][k], vb[r][k], thr4, none, i0, c);
+      }
+      if (WORDS == 4 && w0 + 4 <= nwords) st_stream_v4 (pd, make_uint4 (o[0], o[1], o[2], o[3]));
+      else
+#pragma unroll
+        for (int k = 0; k < WORDS; k++) if (w0 + k < nwords) pd[k] = o[k];
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (width & 3)) {
+    const int i = (nwords << 2) + threadIdx.x;
+    for (int r = 0; r < VF_ROWS; r++) {
+      if (j0 + r >= height) break;
+      const int s1 = a[(size_t) (j0 + r) * old_stride + i], s2 = b[(size_t) (j0 + r) * new_stride + i];
+      uint8_t o = (uint8_t) s2;
+      if ((s2 < s1 - threshold) || (s2 > s1 + threshold)) o = ((i + j0 + r + t) & 4) ? 16 : 240;
+      d[(size_t) (j0 + r) * dst_stride + i] = o;
+    }
+  }
+}
+
+// ---- sum of absolute differences ----------------------------------------------------------------------
+// sums[frame] += SAD of this thread's samples; the accumulator is the reference's orc_uint32: it wraps modulo 2^32
+// (an 8K frame can exceed it), and so does this one (32-bit partial sums, 32-bit atomicAdd).
+template <int WORDS>
+__global__ void __launch_bounds__ (VF_TX * VF_TY)
+sad_kernel (const uint8_t *a, int a_stride, size_t a_fs, const uint8_t *b, int b_stride, size_t b_fs, int width, int height,
+    uint32_t *sums)
+{
+  const int w0 = (blockIdx.x * VF_TX + threadIdx.x) * WORDS;
+  const int j0 = (blockIdx.y * VF_TY + threadIdx.y) * VF_ROWS;
+  const int nwords = width >> 2;
+  const uint8_t *fa = a + (size_t) blockIdx.z * a_fs, *fb = b + (size_t) blockIdx.z * b_fs;
+  uint32_t acc = 0;
+  if (w0 < nwords) {
+    uint32_t va[VF_ROWS][WORDS], vb[VF_ROWS][WORDS];
+#pragma unroll
+    for (int r = 0; r < VF_ROWS; r++) {
+#pragma unroll
+      for (int k = 0; k < WORDS; k++) { va[r][k] = 0; vb[r][k] = 0; }
+      if (j0 + r >= height) continue;
+      const uint32_t *pa = reinterpret_cast<const uint32_t *> (fa + (size_t) (j0 + r) * a_stride) + w0;
+      const uint32_t *pb = reinterpret_cast<const uint32_t *> (fb + (size_t) (j0 + r) * b_stride) + w0;
+      if (WORDS == 4 && w0 + 4 <= nwords) {
+        const uint4 qa = ld_stream_v4 (pa), qb = ld_stream_v4 (pb);
+        va[r][0] = qa.x; va[r][1] = qa.y; va[r][2] = qa.z; va[r][3] = qa.w;
+        vb[r][0] = qb.x; vb[r][1] = qb.y; vb[r][2] = qb.z; vb[r][3] = qb.w;
+      } else
+#pragma unroll
+        for (int k = 0; k < WORDS; k++) if (w0 + k < nwords) { va[r][k] = ldg_u32 (pa + k); vb[r][k] = ldg_u32 (pb + k); }
+    }
+#pragma unroll
+    for (int r = 0; r < VF_ROWS; r++)
+#pragma unroll
+      for (int k = 0; k < WORDS; k++) acc = __vsadu4 (va[r][k], vb[r][k]) + acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (width & 3)) {
+    const int i = (nwords << 2) + threadIdx.x;
+    for (int r = 0; r < VF_ROWS; r++) {
+      if (j0 + r >= height) break;
+      acc += (uint32_t) abs ((int) fa[(size_t) (j0 + r) * a_stride + i] - (int) fb[(size_t) (j0 + r) * b_stride + i]);
+    }
+  }
+  // CTA reduction: warp shuffles, then one atomic per CTA
+  __shared__ uint32_t part[VF_TX * VF_TY / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync (0xffffffffu, acc, o);
+  const int tid = threadIdx.y * VF_TX + threadIdx.x;
+  if ((tid & 31) == 0) part[tid >> 5] = acc;
+  __syncthreads ();
+  if (tid == 0) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < VF_TX * VF_TY / 32; k++) s += part[k];
+    if (s) atomicAdd (sums + blockIdx.z, s);
+  }
+}
+
+bool aligned16 (const void *p, size_t a, size_t b) { return ((uintptr_t) p) % 16 == 0 && a % 16 == 0 && b % 16 == 0; }
+bool aligned4 (const void *p, size_t a, size_t b) { return ((uintptr_t) p) % 4 == 0 && a % 4 == 0 && b % 4 == 0; }
+
+dim3 vf_grid (int width, int height, int nframes, int words) {
+  const int nwords = width >> 2;
+  int gx = (nwords + VF_TX * words - 1) / (VF_TX * words);
+  if (gx < 1) gx = 1;                                        // width < 4: only the bytewise tail
+  return dim3 (gx, (height + VF_TY * VF_ROWS - 1) / (VF_TY * VF_ROWS), nframes);
+}
+
+}  // namespace
+
+B200VF_API int b200vf_zebrastripe_y_threshold (int threshold) {
+  return 16 + (int) floor (0.5 + 2.19 * threshold);          // gstzebrastripe.c:150-151
+}
+
+B200VF_API int b200vf_zebrastripe (b200vf_ctx *ctx, uint8_t *d_luma, int pixel_stride, int row_stride, size_t frame_stride,
+    int nframes, int width, int height, int y_threshold, int t, void *stream)
+{
+  B200VF_REQUIRE (ctx && d_luma && width > 0 && height > 0 && nframes > 0, B200VF_E_INVAL, "zebrastripe: bad argument");
+  B200VF_REQUIRE (pixel_stride == 1 || pixel_stride == 2 || pixel_stride == 4, B200VF_E_UNSUPPORTED,
+      "zebrastripe: pixel stride %d (1 planar / NV12, 2 YUY2 / UYVY, 4 AYUV)", pixel_stride);
+  B200VF_REQUIRE (row_stride >= width * pixel_stride - (pixel_stride - 1), B200VF_E_INVAL, "zebrastripe: row stride");
+  B200VF_REQUIRE (height <= 65535 * VF_TY * VF_ROWS && nframes <= 65535, B200VF_E_UNSUPPORTED, "zebrastripe: grid limits");
+  cudaStream_t s = b200vf_stream (ctx, stream);
+  const dim3 block (VF_TX, VF_TY);
+  if (pixel_stride == 1 && aligned4 (d_luma, (size_t) row_stride, frame_stride)) {
+    if (aligned16 (d_luma, (size_t) row_stride, frame_stride))
+      zebra_planar_kernel<4><<<vf_grid (width, height, nframes, 4), block, 0, s>>> (d_luma, row_stride, frame_stride, width, height, y_threshold, t);
+    else
+      zebra_planar_kernel<1><<<vf_grid (width, height, nframes, 1), block, 0, s>>> (d_luma, row_stride, frame_stride, width, height, y_threshold, t);
+    return b200vf_launched (ctx, "zebrastripe_planar");
+  }
+  const dim3 grid ((width + VF_TX - 1) / VF_TX, (height + VF_TY * VF_ROWS - 1) / (VF_TY * VF_ROWS), nframes);
+  zebra_packed_kernel<<<grid, block, 0, s>>> (d_luma, pixel_stride, row_stride, frame_stride, width, height, y_threshold, t);
+  return b200vf_launched (ctx, "zebrastripe_packed");
+}
+
+B200VF_API int b200vf_videodiff_luma (b200vf_ctx *ctx, const uint8_t *d_old, int old_stride, size_t old_frame_stride,
+    const uint8_t *d_new, int new_stride, size_t new_frame_stride, uint8_t *d_out, int out_stride, size_t out_frame_stride,
+    int width, int height, int nframes, int threshold, int t, void *stream)
+{
+  B200VF_REQUIRE (ctx && d_old && d_new && d_out && width > 0 && height > 0 && nframes > 0, B200VF_E_INVAL, "videodiff: bad argument");
+  B200VF_REQUIRE (old_stride >= width && new_stride >= width && out_stride >= width, B200VF_E_INVAL, "videodiff: row stride");
+  B200VF_REQUIRE (aligned4 (d_old, (size_t) old_stride, old_frame_stride) && aligned4 (d_new, (size_t) new_stride, new_frame_stride) &&
+      aligned4 (d_out, (size_t) out_stride, out_frame_stride), B200VF_E_INVAL,
+      "videodiff: planes and pitches must be 4-byte aligned (GstVideoInfo rounds luma pitches up to 4)");
+  B200VF_REQUIRE (height <= 65535 * VF_TY * VF_ROWS && nframes <= 65535, B200VF_E_UNSUPPORTED, "videodiff: grid limits");
+  cudaStream_t s = b200vf_stream (ctx, stream);
+  const dim3 block (VF_TX, VF_TY);
+  const bool v16 = aligned16 (d_old, (size_t) old_stride, old_frame_stride) && aligned16 (d_new, (size_t) new_stride, new_frame_stride) &&
+      aligned16 (d_out, (size_t) out_stride, out_frame_stride);
+  if (v16)
+    videodiff_kernel<4><<<vf_grid (width, height, nframes, 4), block, 0, s>>> (d_old, old_stride, old_frame_stride, d_new, new_stride,
+        new_frame_stride, d_out, out_stride, out_frame_stride, width, height, threshold, t);
+  else
+    videodiff_kernel<1><<<vf_grid (width, height, nframes, 1), block, 0, s>>> (d_old, old_stride, old_frame_stride, d_new, new_stride,
+        new_frame_stride, d_out, out_stride, out_frame_stride, width, height, threshold, t);
+  return b200vf_launched (ctx, "videodiff_luma");
+}
+
+B200VF_API int b200vf_sad_u8 (b200vf_ctx *ctx, const uint8_t *d_a, int a_stride, size_t a_frame_stride, const uint8_t *d_b,
+    int b_stride, size_t b_frame_stride, int width, int height, int nframes, uint32_t *d_sums, void *stream)
+{
+  B200VF_REQUIRE (ctx && d_a && d_b && d_sums && width > 0 && height > 0 && nframes > 0, B200VF_E_INVAL, "sad_u8: bad argument");
+  B200VF_REQUIRE (a_stride >= width && b_stride >= width, B200VF_E_INVAL, "sad_u8: row stride");
+  B200VF_REQUIRE (aligned4 (d_a, (size_t) a_stride, a_frame_stride) && aligned4 (d_b, (size_t) b_stride, b_frame_stride), B200VF_E_INVAL,
+      "sad_u8: planes and pitches must be 4-byte aligned");
+  B200VF_REQUIRE (height <= 65535 * VF_TY * VF_ROWS && nframes <= 65535, B200VF_E_UNSUPPORTED, "sad_u8: grid limits");
+  cudaStream_t s = b200vf_stream (ctx, stream);
+  B200VF_CHECK_CUDA (cudaMemsetAsync (d_sums, 0, sizeof (uint32_t) * (size_t) nframes, s));
+  const dim3 block (VF_TX, VF_TY);
+  if (aligned16 (d_a, (size_t) a_stride, a_frame_stride) && aligned16 (d_b, (size_t) b_stride, b_frame_stride))
+    sad_kernel<4><<<vf_grid (width, height, nframes, 4), block, 0, s>>> (d_a, a_stride, a_frame_stride, d_b, b_stride, b_frame_stride,
+        width, height, d_sums);
+  else
+    sad_kernel<1><<<vf_grid (width, height, nframes, 1), block, 0, s>>> (d_a, a_stride, a_frame_stride, d_b, b_stride, b_frame_stride,
+        width, height, d_sums);
+  return b200vf_launched (ctx, "sad_u8");
+}
+
+// gst_scene_change_transform_frame_ip, gstscenechange.c:196-236: the decision on the frame score
+// (score = SAD / (width * height), :154). Host arithmetic on five doubles, statement for statement.
+B200VF_API int b200vf_scenechange_reset (b200vf_scenechange_state *st) {
+  B200VF_REQUIRE (st, B200VF_E_INVAL, "scenechange_reset: NULL");
+  st->n_diffs = 0;
+  for (int i = 0; i < B200VF_SC_N_DIFFS; i++) st->diffs[i] = 0.0;
+  return B200VF_OK;
+}
+B200VF_API int b200vf_scenechange_update (b200vf_scenechange_state *st, double score, int *change_out) {
+  B200VF_REQUIRE (st && change_out, B200VF_E_INVAL, "scenechange_update: NULL");
+  const int N = B200VF_SC_N_DIFFS;
+  for (int i = 0; i < N - 1; i++) st->diffs[i] = st->diffs[i + 1];     // memmove (:200-201)
+  st->diffs[N - 1] = score;
+  st->n_diffs++;
+  double score_min = st->diffs[0], score_max = st->diffs[0];
+  for (int i = 1; i < N - 1; i++) {
+    score_min = score_min < st->diffs[i] ? score_min : st->diffs[i];     // MIN (score_min, diffs[i])
+    score_max = score_max > st->diffs[i] ? score_max : st->diffs[i];     // MAX (score_max, diffs[i])
+  }
+  const double threshold = 1.8 * score_max - 0.8 * score_min;
+  int change;
+  if (st->n_diffs > (N - 1)) {
+    if (score < 5) change = 0;
+    else if (score / threshold < 1.0) change = 0;
+    else if ((score > 30) && (score / st->diffs[N - 2] > 1.4)) change = 1;
+    else if (score / threshold > 2.3) change = 1;
+    else if (score > 50) change = 1;
+    else change = 0;
+  } else change = 0;
+  if (change) b200vf_scenechange_reset (st);
+  *change_out = change;
+  return B200VF_OK;
+}

@@ -248,6 +248,43 @@ int b200vf_gt_unpack_index (const void *packed, size_t size, int width, int heig
 int b200vf_remap_packed (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, const void *d_packed,
     int width, int height, size_t frame_stride, int nframes, uint32_t fill, void *stream);
 
+/* ---------------------------------------------------- videofiltersbad plugin
+ * (sibling per-pixel filters on planar / packed YUV.)
+ *
+ * zebrastripe: gst_zebra_stripe_transform_frame_ip (gst/videofilters/
+ * gstzebrastripe.c:205-253), in place on the luma samples. d_luma = the first
+ * luma byte of frame 0, i.e. plane 0 + the format's byte offset (+1 for UYVY
+ * and AYUV, :232-237); pixel_stride = GST_VIDEO_FORMAT_INFO_PSTRIDE (finfo, 0):
+ * 1 (I420 Y444 Y42B Y41B NV12 NV21 YV12), 2 (YUY2 UYVY), 4 (AYUV). y_threshold
+ * = b200vf_zebrastripe_y_threshold (`threshold` property, int [0,100] = 90,
+ * :150-151). t = the element's frame counter (:217); frame f of a batch uses
+ * t + f. */
+int b200vf_zebrastripe_y_threshold (int threshold);
+int b200vf_zebrastripe (b200vf_ctx *ctx, uint8_t *d_luma, int pixel_stride, int row_stride, size_t frame_stride,
+    int nframes, int width, int height, int y_threshold, int t, void *stream);
+/* videodiff: the luma loop of gst_video_diff_transform_frame_ip_planarY
+ * (gstvideodiff.c:94-117): out = |new - old| > threshold ? ((i+j+t)&4 ? 16 :
+ * 240) : new. threshold = 10 and t = 0 in the element (:89, never counted up).
+ * The chroma planes are plain copies (:118-127): cudaMemcpy2DAsync in the
+ * shell. Planes and pitches 4-byte aligned (GstVideoInfo pitches are). */
+int b200vf_videodiff_luma (b200vf_ctx *ctx, const uint8_t *d_old, int old_stride, size_t old_frame_stride,
+    const uint8_t *d_new, int new_stride, size_t new_frame_stride, uint8_t *d_out, int out_stride, size_t out_frame_stride,
+    int width, int height, int nframes, int threshold, int t, void *stream);
+/* scenechange: orc_sad_nxm_u8 (gstscenechangeorc.orc; C backup
+ * gstscenechangeorc-dist.c:147-180) for each of nframes pairs of luma planes:
+ * d_sums[f] = sum |a - b| modulo 2^32 (the reference accumulates in
+ * orc_uint32). Device result; copy it out after the stream has run.
+ * get_frame_score (gstscenechange.c:141-155) = sum / (width * height). */
+int b200vf_sad_u8 (b200vf_ctx *ctx, const uint8_t *d_a, int a_stride, size_t a_frame_stride, const uint8_t *d_b,
+    int b_stride, size_t b_frame_stride, int width, int height, int nframes, uint32_t *d_sums, void *stream);
+/* The decision that follows the score (gstscenechange.c:196-236): host state
+ * of SC_N_DIFFS = 5 scores; *change_out = 1 when the element would push its
+ * force-key-unit event. reset = the state of a fresh element / after a change. */
+#define B200VF_SC_N_DIFFS 5
+typedef struct b200vf_scenechange_state { double diffs[B200VF_SC_N_DIFFS]; int n_diffs; } b200vf_scenechange_state;
+int b200vf_scenechange_reset (b200vf_scenechange_state *st);
+int b200vf_scenechange_update (b200vf_scenechange_state *st, double score, int *change_out);
+
 /* ------------------------------------------------------------ fused chains
  * bayer2rgb followed by per-channel LUT elements (coloreffects per-channel
  * presets, burn, dodge, chromium, solarize, composed on the host) and/or one

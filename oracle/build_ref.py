@@ -403,6 +403,71 @@ def gt_tu(name):
     return gen
 
 
+# ------------------------------------------------------------- videofilters
+GV = "gst/videofilters/"
+VF_FRAME_SHIM = """
+typedef int GstFlowReturn;
+#define GST_FLOW_OK 0
+typedef struct { struct { int width, height; int stride[4]; int comp_w[4], comp_h[4]; } info; void *data[4]; } GstVideoFrame;
+#define GST_VIDEO_FRAME_COMP_HEIGHT(f,c) ((f)->info.comp_h[c])
+#define GST_VIDEO_FRAME_COMP_WIDTH(f,c) ((f)->info.comp_w[c])
+"""
+TUS["ref_zebrastripe.c"] = lambda: (
+    "#include <glib.h>\n"
+    "/* data0 = frame->data[0]; offset / y_position / pixel_stride as the format switch sets them (:219-240) */\n"
+    "void ref_zebrastripe (guint8 *data0, int stride0, int width, int height, int threshold, int t,\n"
+    "    int offset, int pixel_stride, int y_position)\n{\n  int i, j;\n"
+    "  struct { void *data[1]; struct { int stride[1]; } info; } fr, *frame = &fr;\n"
+    "  fr.data[0] = data0; fr.info.stride[0] = stride0;\n"
+    # the per-pixel loop, gstzebrastripe.c:242-250
+    + between(GV + "gstzebrastripe.c", r"^  for \(j = 0; j < height; j\+\+\) \{", r"^  }$")
+    + "}\n"
+    # y_threshold from the property (:150-151)
+    + "int ref_zebrastripe_y_threshold (int threshold)\n{\n  struct { int threshold, y_threshold; } z, *zebrastripe = &z;\n"
+    "  z.threshold = threshold;\n"
+    + between(GV + "gstzebrastripe.c", r"^      zebrastripe->y_threshold =$", r"2\.19 \* zebrastripe->threshold\);")
+    + "  return z.y_threshold;\n}\n")
+
+TUS["ref_videodiff.c"] = lambda: (
+    "#include <glib.h>\n" + VF_FRAME_SHIM
+    + "typedef struct { int threshold; int t; } GstVideoDiff;\n"
+    + func(GV + "gstvideodiff.c", "gst_video_diff_transform_frame_ip_planarY")
+    + """
+/* three planes each; comp_w/comp_h = GST_VIDEO_FRAME_COMP_WIDTH/HEIGHT of planes 1 and 2 */
+void ref_videodiff (guint8 *out[3], guint8 *in[3], guint8 *old[3], const int stride[3], int width, int height,
+    int cw, int ch, int threshold, int t)
+{
+  GstVideoDiff vd = { threshold, t };
+  GstVideoFrame o, n, p;
+  GstVideoFrame *fr[3] = { &o, &n, &p };
+  guint8 **pl[3] = { out, in, old };
+  for (int f = 0; f < 3; f++) {
+    fr[f]->info.width = width; fr[f]->info.height = height;
+    for (int k = 0; k < 3; k++) {
+      fr[f]->data[k] = pl[f][k]; fr[f]->info.stride[k] = stride[k];
+      fr[f]->info.comp_w[k] = k ? cw : width; fr[f]->info.comp_h[k] = k ? ch : height;
+    }
+  }
+  gst_video_diff_transform_frame_ip_planarY (&vd, &o, &n, &p);
+}
+""")
+
+TUS["ref_scenechange.c"] = lambda: (
+    "#include <glib.h>\n"
+    "void orc_sad_nxm_u8 (guint32 * a1, const guint8 * s1, int s1_stride, const guint8 * s2, int s2_stride, int n, int m);\n"
+    "#define SC_N_DIFFS 5\n"
+    "typedef struct { int n_diffs; double diffs[SC_N_DIFFS]; } GstSceneChange;\n"
+    "/* get_frame_score, gstscenechange.c:141-155 */\n"
+    "double ref_scenechange_score (const guint8 *a, int a_stride, const guint8 *b, int b_stride, int width, int height, guint32 *sad)\n"
+    "{\n  guint32 score = 0;\n  orc_sad_nxm_u8 (&score, a, a_stride, b, b_stride, width, height);\n  if (sad) *sad = score;\n"
+    "  return ((double) score) / (width * height);\n}\n"
+    "/* the decision, :196-236; state = { n_diffs, diffs[5] } */\n"
+    "int ref_scenechange_update (GstSceneChange *scenechange, double score)\n{\n"
+    "  double score_min, score_max, threshold;\n  gboolean change;\n  int i;\n"
+    + between(GV + "gstscenechange.c", r"^  memmove \(scenechange->diffs, scenechange->diffs \+ 1,$", r"^    scenechange->n_diffs = 0;$")
+    + "  }\n  return change;\n}\n")
+
+
 def register_gt_tus():
     for name in GT_ELEMENTS:
         TUS["ref_gt_%s.c" % name] = gt_tu(name)
@@ -417,7 +482,8 @@ def build(verbose=False):
     with tempfile.TemporaryDirectory(prefix="b200vf_ref_") as tmp:
         objs = []
         # ORC C backups, compiled where they lie
-        for rel in ("gst/bayer/gstbayerorc-dist.c", "gst/gaudieffects/gstgaudieffectsorc-dist.c"):
+        for rel in ("gst/bayer/gstbayerorc-dist.c", "gst/gaudieffects/gstgaudieffectsorc-dist.c",
+                    "gst/videofilters/gstscenechangeorc-dist.c"):
             o = os.path.join(tmp, os.path.basename(rel) + ".o")
             subprocess.check_call(["gcc"] + CFLAGS + ["-c", os.path.join(REF, rel), "-o", o])
             objs.append(o)

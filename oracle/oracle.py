@@ -198,6 +198,34 @@ class Port(_Base):
                               frame.shape[1], OFF_EDGE[off_edge], int(is_ayuv))
         return out
 
+    # ---- videofilters ------------------------------------
+    def zebrastripe(self, frame, width, height, threshold=90, t=0, pixel_stride=1, luma_offset=0):
+        """frame: uint8 [rows, stride] holding plane 0 (or the packed frame); luma sample of pixel i of row j =
+        byte luma_offset + i*pixel_stride of row j. Returns the striped copy."""
+        out = _u8(frame).copy()
+        self.lib.oracle_zebrastripe(C.c_void_p(out.ctypes.data + luma_offset), pixel_stride, out.shape[1], width, height,
+                                    self.lib.oracle_zebrastripe_y_threshold(threshold), t)
+        return out
+
+    def videodiff_luma(self, old, new, width, height, threshold=10, t=0):
+        old, new = _u8(old), _u8(new)
+        out = new.copy()
+        self.lib.oracle_videodiff_luma(_p(out), _p(new), _p(old), new.shape[1], width, height, threshold, t)
+        return out
+
+    def sad_u8(self, a, b, width, height):
+        a, b = _u8(a), _u8(b)
+        self.lib.oracle_sad_u8.restype = C.c_uint32
+        return int(self.lib.oracle_sad_u8(_p(a), a.shape[1], _p(b), b.shape[1], width, height))
+
+    def scenechange_run(self, scores):
+        """the element's decision over a sequence of frame scores -> list of bools"""
+        class S(C.Structure):
+            _fields_ = [("n_diffs", C.c_int), ("diffs", C.c_double * 5)]
+        st = S()
+        self.lib.oracle_scenechange_update.argtypes = [C.c_void_p, C.c_double]
+        return [bool(self.lib.oracle_scenechange_update(C.byref(st), float(x))) for x in scores]
+
 
 class _GT(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("pixel_stride", C.c_int), ("row_stride", C.c_int),
@@ -338,6 +366,43 @@ class Ref(_Base):
         gmap = np.ascontiguousarray(gmap, np.float64)
         self.lib.ref_gt_apply_map(C.byref(gt), _p(gmap), _p(frame), _p(out), C.c_size_t(out.size), int(is_ayuv))
         return out
+
+    # ---- videofilters ------------------------------------
+    def zebrastripe(self, frame, width, height, threshold=90, t=0, pixel_stride=1, luma_offset=0):
+        """the reference's loop works from frame->data[0] with (offset, pixel_stride, y_position): UYVY has
+        offset 1, AYUV y_position 1 (gstzebrastripe.c:232-237); both are `luma_offset` here."""
+        out = _u8(frame).copy()
+        off, ypos = (0, luma_offset) if pixel_stride == 4 else (luma_offset, 0)
+        self.lib.ref_zebrastripe(_p(out), out.shape[1], width, height, self.lib.ref_zebrastripe_y_threshold(threshold), t,
+                                 off, pixel_stride, ypos)
+        return out
+
+    def videodiff_luma(self, old, new, width, height, threshold=10, t=0):
+        """through the reference's three-plane function with 1x1 dummy chroma planes"""
+        old, new = _u8(old), _u8(new)
+        out = np.zeros_like(new)
+        dummy = [np.zeros((1, 4), np.uint8) for _ in range(6)]
+        P = C.c_void_p * 3
+        outs = P(out.ctypes.data, dummy[0].ctypes.data, dummy[1].ctypes.data)
+        ins = P(new.ctypes.data, dummy[2].ctypes.data, dummy[3].ctypes.data)
+        olds = P(old.ctypes.data, dummy[4].ctypes.data, dummy[5].ctypes.data)
+        strides = (C.c_int * 3)(new.shape[1], 4, 4)
+        self.lib.ref_videodiff(outs, ins, olds, strides, width, height, 1, 1, threshold, t)
+        return out
+
+    def sad_u8(self, a, b, width, height):
+        a, b = _u8(a), _u8(b)
+        sad = C.c_uint32(0)
+        self.lib.ref_scenechange_score.restype = C.c_double
+        self.lib.ref_scenechange_score(_p(a), a.shape[1], _p(b), b.shape[1], width, height, C.byref(sad))
+        return int(sad.value)
+
+    def scenechange_run(self, scores):
+        class S(C.Structure):
+            _fields_ = [("n_diffs", C.c_int), ("diffs", C.c_double * 5)]
+        st = S()
+        self.lib.ref_scenechange_update.argtypes = [C.c_void_p, C.c_double]
+        return [bool(self.lib.ref_scenechange_update(C.byref(st), float(x))) for x in scores]
 
 
 _cache = {}

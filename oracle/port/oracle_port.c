@@ -500,3 +500,77 @@ oracle_map_fisheye (double *map, int width, int height)
       map[1] = 0.5 * (ny + 1.0) * h;
     }
 }
+
+/* --------------------------------------------------- videofilters
+ * zebrastripe: gst/videofilters/gstzebrastripe.c:242-250 (loop), :150-151 (threshold).
+ * luma = first luma byte (plane 0 + offset + y_position), ps = pixel stride. */
+EXPORT int
+oracle_zebrastripe_y_threshold (int threshold)
+{
+  return 16 + (int) floor (0.5 + 2.19 * threshold);
+}
+
+EXPORT void
+oracle_zebrastripe (uint8_t *luma, int ps, int stride, int width, int height, int y_threshold, int t)
+{
+  for (int j = 0; j < height; j++)
+    for (int i = 0; i < width; i++) {
+      uint8_t *p = luma + (size_t) j * stride + (size_t) i * ps;
+      if (*p >= y_threshold && ((i + j + t) & 0x4)) *p = 16;
+    }
+}
+
+/* videodiff luma loop: gst/videofilters/gstvideodiff.c:101-117 */
+EXPORT void
+oracle_videodiff_luma (uint8_t *out, const uint8_t *cur, const uint8_t *old, int stride, int width, int height,
+    int threshold, int t)
+{
+  for (int j = 0; j < height; j++)
+    for (int i = 0; i < width; i++) {
+      int s1 = old[(size_t) j * stride + i], s2 = cur[(size_t) j * stride + i];
+      uint8_t v = (uint8_t) s2;
+      if ((s2 < s1 - threshold) || (s2 > s1 + threshold)) v = ((i + j + t) & 0x4) ? 16 : 240;
+      out[(size_t) j * stride + i] = v;
+    }
+}
+
+/* orc_sad_nxm_u8 (`accsadubl`, gstscenechangeorc.orc; 32-bit accumulator) */
+EXPORT uint32_t
+oracle_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride, int width, int height)
+{
+  uint32_t acc = 0;
+  for (int j = 0; j < height; j++)
+    for (int i = 0; i < width; i++) {
+      int d = (int) a[(size_t) j * a_stride + i] - (int) b[(size_t) j * b_stride + i];
+      acc += (uint32_t) (d < 0 ? -d : d);
+    }
+  return acc;
+}
+
+/* scenechange decision, gst/videofilters/gstscenechange.c:196-236.
+ * state = { int n_diffs; double diffs[5]; } (the element's fields, :43-44) */
+typedef struct { int n_diffs; double diffs[5]; } oracle_scenechange;
+EXPORT int
+oracle_scenechange_update (oracle_scenechange *sc, double score)
+{
+  int change;
+  memmove (sc->diffs, sc->diffs + 1, sizeof (double) * 4);
+  sc->diffs[4] = score;
+  sc->n_diffs++;
+  double lo = sc->diffs[0], hi = sc->diffs[0];
+  for (int i = 1; i < 4; i++) {
+    lo = lo < sc->diffs[i] ? lo : sc->diffs[i];
+    hi = hi > sc->diffs[i] ? hi : sc->diffs[i];
+  }
+  double threshold = 1.8 * hi - 0.8 * lo;
+  if (sc->n_diffs > 4) {
+    if (score < 5) change = 0;
+    else if (score / threshold < 1.0) change = 0;
+    else if (score > 30 && score / sc->diffs[3] > 1.4) change = 1;
+    else if (score / threshold > 2.3) change = 1;
+    else if (score > 50) change = 1;
+    else change = 0;
+  } else change = 0;
+  if (change) { memset (sc->diffs, 0, sizeof sc->diffs); sc->n_diffs = 0; }
+  return change;
+}

@@ -5,6 +5,7 @@ Run where /root/reference is mounted (this container):   python tests/golden/mak
   * golden_small.npz         - seeded inputs + outputs of the reference's own C (oracle/_ref, built by
                                oracle/build_ref.py from /root/reference) for every op of the hot path;
   * coloreffects_tables.npz  - the five 256x3 preset tables (data of gstcoloreffects.c:117-286);
+  * golden_videofilters.npz  - the same for zebrastripe / videodiff / scenechange (SURVEY 8f rank 4);
   * element_surface.json     - factory name -> properties (type/min/max/default) and pad-template formats,
                                extracted from the reference's docs/plugins/gst_plugins_cache.json.
 The reference's tests hold no vectors for these elements, so these fixtures are what pins
@@ -25,7 +26,40 @@ import refprops        # noqa: E402
 REF = os.environ.get("B200VF_REFERENCE", "/root/reference")
 
 
+def make_videofilters():
+    """golden_videofilters.npz: the videofiltersbad plugin's loops through the reference's C"""
+    R = oracle.get("reference")
+    rng = np.random.default_rng(20261017)
+    g = {}
+    w, h = 22, 13
+    st = oracle.round_up_4(w)
+    a = rng.integers(0, 256, (h, st), dtype=np.uint8)
+    b = a.copy()
+    m = rng.random((h, st)) < 0.4
+    b[m] = rng.integers(0, 256, int(m.sum()), dtype=np.uint8)
+    g["luma_a"], g["luma_b"] = a, b
+    for thr in (0, 50, 90, 100):
+        for t in (0, 3):
+            g["zebra_%d_%d" % (thr, t)] = R.zebrastripe(a, w, h, thr, t)
+    yuy2 = rng.integers(0, 256, (h, oracle.round_up_4(2 * w)), dtype=np.uint8)
+    ayuv = rng.integers(0, 256, (h, 4 * w), dtype=np.uint8)
+    g["yuy2"], g["ayuv"] = yuy2, ayuv
+    g["zebra_yuy2"] = R.zebrastripe(yuy2, w, h, 40, 2, 2, 0)
+    g["zebra_uyvy"] = R.zebrastripe(yuy2, w, h, 40, 2, 2, 1)
+    g["zebra_ayuv"] = R.zebrastripe(ayuv, w, h, 40, 2, 4, 1)
+    for t in (0, 5):
+        g["videodiff_%d" % t] = R.videodiff_luma(a, b, w, h, 10, t)
+    g["sad"] = np.array([R.sad_u8(a, b, w, h)], np.uint32)
+    scores = np.concatenate([rng.uniform(0, 8, 30), [70.0], rng.uniform(0, 8, 8), [33.0, 2, 2, 2, 2, 2, 90, 100],
+                             rng.uniform(20, 60, 20)])
+    g["sc_scores"] = scores
+    g["sc_changes"] = np.array(R.scenechange_run(scores), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "golden_videofilters.npz"), **g)
+    print("golden_videofilters.npz: %d arrays" % len(g))
+
+
 def main():
+    make_videofilters()
     R = oracle.get("reference")
     rng = np.random.default_rng(20260925)
     g = {}
@@ -115,6 +149,10 @@ def main():
     json.dump(surf, open(os.path.join(HERE, "element_surface.json"), "w"), indent=1, sort_keys=True)
     print("wrote %d arrays, %d elements" % (len(g), len(surf)))
 
+
+if __name__ == "__main__" and "--videofilters" in sys.argv:
+    make_videofilters()
+    sys.exit(0)
 
 if __name__ == "__main__":
     main()

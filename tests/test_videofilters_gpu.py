@@ -1,0 +1,118 @@
+"""videofiltersbad plugin: zebrastripe, videodiff (luma loop), scenechange (SAD + decision)
+through the C-ABI, bit-exact against the oracle."""
+import numpy as np
+import pytest
+
+import frames
+
+pytestmark = pytest.mark.gpu
+
+# widths: < 4 (bytewise tail only), not a multiple of 4, pitch not 16-byte aligned (642 -> 644), aligned, > one CTA
+SIZES = [(3, 5), (7, 5), (22, 13), (130, 21), (642, 33), (1024, 40), (3840, 18)]
+
+
+def up(ctx, a):
+    return ctx.upload(np.ascontiguousarray(a))
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+def test_zebrastripe_planar(ctx, orc, rng, w, h):
+    st = frames.round_up_4(w)
+    fr = frames.random_u8(rng, h, st)
+    for thr in (0, 37, 90, 100):
+        for t in (0, 1, 6):
+            d = up(ctx, fr)
+            ctx.zebrastripe(d, 1, st, w, h, threshold=thr, t=t)
+            got = ctx.download(d, fr.size).reshape(h, st)
+            want = orc.zebrastripe(fr, w, h, thr, t)
+            assert np.array_equal(got, want), (w, h, thr, t, ctx.last_kernel(), np.argwhere(got != want)[:4])
+
+
+@pytest.mark.parametrize("w,h", [(7, 5), (130, 21), (640, 24)])
+def test_zebrastripe_packed_formats(ctx, orc, rng, w, h):
+    """YUY2 (luma at even bytes), UYVY (odd bytes), AYUV (byte 1 of 4): only the luma bytes may change"""
+    for ps, off, stride in [(2, 0, frames.round_up_4(2 * w)), (2, 1, frames.round_up_4(2 * w)), (4, 1, 4 * w)]:
+        fr = frames.random_u8(rng, h, stride)
+        d = up(ctx, fr)
+        ctx.zebrastripe(d.ptr + off, ps, stride, w, h, threshold=45, t=3)
+        got = ctx.download(d, fr.size).reshape(h, stride)
+        want = orc.zebrastripe(fr, w, h, 45, 3, ps, off)
+        assert np.array_equal(got, want), (w, h, ps, off)
+
+
+def test_zebrastripe_batch_counts_t_per_frame(ctx, orc, rng):
+    w, h, n = 256, 32, 5
+    fr = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    d = up(ctx, fr)
+    ctx.zebrastripe(d, 1, w, w, h, threshold=50, t=2, nframes=n)
+    got = ctx.download(d, fr.size).reshape(n, h, w)
+    for f in range(n):
+        assert np.array_equal(got[f], orc.zebrastripe(fr[f], w, h, 50, 2 + f)), f
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+def test_videodiff_luma(ctx, orc, rng, w, h):
+    st = frames.round_up_4(w)
+    old = frames.random_u8(rng, h, st)
+    new = old.copy()
+    m = rng.random((h, st)) < 0.5
+    new[m] = (old[m].astype(int) + rng.integers(-30, 31, int(m.sum()))).clip(0, 255).astype(np.uint8)
+    for thr, t in [(10, 0), (10, 5), (0, 1), (254, 0), (255, 0), (300, 2), (-1, 3)]:
+        d_out = ctx.alloc(old.size)
+        ctx.videodiff_luma(up(ctx, old), up(ctx, new), d_out, st, w, h, threshold=thr, t=t)
+        got = ctx.download(d_out, old.size).reshape(h, st)[:, :w]
+        want = orc.videodiff_luma(old, new, w, h, thr, t)[:, :w]
+        assert np.array_equal(got, want), (w, h, thr, t, np.argwhere(got != want)[:4])
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+def test_sad_u8(ctx, orc, rng, w, h):
+    st = frames.round_up_4(w)
+    n = 3
+    a = rng.integers(0, 256, (n, h, st), dtype=np.uint8)
+    b = rng.integers(0, 256, (n, h, st), dtype=np.uint8)
+    b[1] = a[1]                                            # identical pair: 0
+    d_sums = ctx.alloc(4 * n)
+    ctx.sad_u8(up(ctx, a), up(ctx, b), st, w, h, d_sums, nframes=n)
+    got = ctx.download(d_sums, 4 * n).view(np.uint32)
+    want = [orc.sad_u8(a[i], b[i], w, h) for i in range(n)]
+    assert list(got) == want, (w, h)
+
+
+def test_sad_u8_wraps_like_the_32_bit_accumulator(ctx, orc):
+    """8K luma planes of 0 and 255 differ by 255 * 33.2 M = 8.46e9 > 2^32: the reference's orc_uint32 wraps,
+    and so must the device sum (size-independent property: the sum is linear in the number of identical rows)"""
+    w, h = 7680, 4320
+    a = np.zeros((h, w), np.uint8)
+    b = np.full((h, w), 255, np.uint8)
+    d_sums = ctx.alloc(4)
+    ctx.sad_u8(up(ctx, a), up(ctx, b), w, w, h, d_sums)
+    got = int(ctx.download(d_sums, 4).view(np.uint32)[0])
+    assert got == (255 * w * h) % (1 << 32)
+    assert got == orc.sad_u8(a[:1], b[:1], w, 1) * h % (1 << 32)
+
+
+def test_scenechange_scores_from_device_sads(ctx, vf, orc, rng):
+    """the element end to end on a synthetic clip: luma planes drift slowly, with two hard cuts; the score is
+    SAD / (w * h) from the device, the decision the library's host state machine; both equal the oracle's"""
+    w, h, n = 320, 180, 40
+    base = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    clip = []
+    for f in range(n):
+        if f in (17, 31):
+            base = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        noise = rng.integers(-3, 4, (h, w))
+        base = (base.astype(int) + noise).clip(0, 255).astype(np.uint8)
+        clip.append(base)
+    clip = np.stack(clip)
+    d = up(ctx, clip)
+    d_sums = ctx.alloc(4 * (n - 1))
+    # pair f = (frame f, frame f + 1): one batched launch, the old frame is the previous one of the same slab
+    ctx.sad_u8(d, d.ptr + h * w, w, w, h, d_sums, nframes=n - 1, frame_stride=h * w)
+    sads = ctx.download(d_sums, 4 * (n - 1)).view(np.uint32)
+    assert list(sads) == [orc.sad_u8(clip[f], clip[f + 1], w, h) for f in range(n - 1)]
+    scores = [float(s) / (w * h) for s in sads]
+    st = vf.SceneChange()
+    got = [st.update(x) for x in scores]
+    assert got == orc.scenechange_run(scores)
+    assert [i + 1 for i, c in enumerate(got) if c] == [17, 31]
