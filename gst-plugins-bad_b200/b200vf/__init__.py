@@ -116,6 +116,7 @@ _SIGS = {
     "b200vf_element_unit_size": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "b200vf_element_transform_host": (_i, [_vp, _vp, _vp, _i]),
     "b200vf_element_transform_device": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "b200vf_element_last_events": (_i, [_vp, _vp, _i]),
 }
 
 MISSING = []
@@ -558,6 +559,15 @@ class Element:
 
     def transform_device(self, d_in, d_out, nframes=1, stream=None):
         check(lib.b200vf_element_transform_device(self.h, _ptr(d_in), _ptr(d_out), nframes, stream))
+
+    def last_events(self):
+        """scenechange: per frame of the last transform call, True where the reference pushes its force-key-unit event"""
+        n = lib.b200vf_element_last_events(self.h, None, 0)
+        if n < 0:
+            check(n)
+        flags = (C.c_int * max(n, 1))()
+        lib.b200vf_element_last_events(self.h, flags, n)
+        return [bool(flags[i]) for i in range(n)]
 
 
 class SceneChange:

@@ -22,7 +22,7 @@
 namespace {
 
 enum Kind { K_BAYER2RGB, K_RGB2BAYER, K_BURN, K_CHROMIUM, K_DILATE, K_DODGE, K_EXCLUSION, K_GAUSSBLUR, K_SOLARIZE,
-  K_COLOREFFECTS, K_CHROMAHOLD, K_GEOMETRIC };
+  K_COLOREFFECTS, K_CHROMAHOLD, K_GEOMETRIC, K_ZEBRASTRIPE, K_VIDEODIFF, K_SCENECHANGE };
 
 struct FormatDef { const char *name; int pstride; int off[4]; /* R,G,B,A (or Y,U,V,A) poffsets; -1 = none */ };
 // gst-plugins-base video-format.c packed layouts (byte offsets in memory)
@@ -33,6 +33,32 @@ const FormatDef kFormats[] = {
   { "GRAY8", 1, { 0, -1, -1, -1 } }, { "GRAY16_BE", 2, { 0, -1, -1, -1 } }, { "GRAY16_LE", 2, { 0, -1, -1, -1 } },
 };
 const char *kBayerFormats[] = { "bggr", "gbrg", "grbg", "rggb" };   // enum order gstbayer2rgb.c:95-101
+
+// YUV layouts of the videofiltersbad elements: where the luma samples are (byte offset of the first one in plane 0,
+// pixel stride) and the default GstVideoInfo geometry (gst-plugins-base video-info.c fill_planes - external to the
+// reference tree like the packed offsets above: the C-ABI takes pointers and pitches, only this mirror computes them).
+struct YuvDef { const char *name; int luma_off, luma_ps; };
+const YuvDef kYuvFormats[] = {
+  { "I420", 0, 1 }, { "YV12", 0, 1 }, { "Y444", 0, 1 }, { "Y42B", 0, 1 }, { "Y41B", 0, 1 }, { "NV12", 0, 1 }, { "NV21", 0, 1 },
+  { "YUY2", 0, 2 }, { "UYVY", 1, 2 }, { "AYUV", 1, 4 },
+};
+const YuvDef *find_yuv (const char *n) {
+  for (const auto &f : kYuvFormats) if (!strcmp (f.name, n)) return &f;
+  return nullptr;
+}
+int round_up (int n, int a) { return (n + a - 1) / a * a; }
+// plane-0 pitch and total frame size
+void yuv_geometry (const char *fmt, int w, int h, int *stride0, size_t *size) {
+  const int s0 = round_up (w, 4), h2 = round_up (h, 2);
+  *stride0 = s0;
+  if (!strcmp (fmt, "I420") || !strcmp (fmt, "YV12")) *size = (size_t) s0 * h2 + 2 * (size_t) round_up (round_up (w, 2) / 2, 4) * (h2 / 2);
+  else if (!strcmp (fmt, "Y444")) *size = 3 * (size_t) s0 * h;
+  else if (!strcmp (fmt, "Y42B")) *size = ((size_t) s0 + round_up (w, 8)) * h;
+  else if (!strcmp (fmt, "Y41B")) *size = ((size_t) s0 + round_up (w, 16) / 2) * h;
+  else if (!strcmp (fmt, "NV12") || !strcmp (fmt, "NV21")) *size = (size_t) s0 * h2 + (size_t) s0 * (h2 / 2);
+  else if (!strcmp (fmt, "YUY2") || !strcmp (fmt, "UYVY")) { *stride0 = round_up (w * 2, 4); *size = (size_t) *stride0 * h; }
+  else { *stride0 = w * 4; *size = (size_t) w * 4 * h; }     // AYUV
+}
 
 const FormatDef *find_format (const char *n) {
   for (const auto &f : kFormats) if (!strcmp (f.name, n)) return &f;
@@ -46,8 +72,10 @@ int find_bayer (const char *n) {
 enum PType { P_UINT, P_INT, P_BOOL, P_DOUBLE, P_ENUM };
 struct PropDef {
   const char *name; PType type; double lo, hi, def; std::vector<const char *> nicks;
-  // GST_PARAM_CONTROLLABLE on everything except the enum presets/modes and perspective's matrix (API dump)
-  bool controllable () const { return !(type == P_ENUM && (!strcmp (name, "preset") || !strcmp (name, "mode"))) && strncmp (name, "matrix-", 7) != 0; }
+  bool ctl = true;
+  // GST_PARAM_CONTROLLABLE on everything except the enum presets/modes, perspective's matrix and zebrastripe's
+  // threshold (API dump)
+  bool controllable () const { return ctl && !(type == P_ENUM && (!strcmp (name, "preset") || !strcmp (name, "mode"))) && strncmp (name, "matrix-", 7) != 0; }
 };
 
 struct ElementMeta { const char *factory, *plugin, *plugin_description, *plugin_license, *type_name, *parent_type_name,
@@ -125,6 +153,11 @@ const std::vector<FactoryDef> &factories () {
         { "matrix-8", P_DOUBLE, -kMaxD, kMaxD, 1, {} } }), false, 0 },
     { "marble", K_GEOMETRIC, kGeo, geo (1, false, { { "x-scale", P_DOUBLE, 0, kMaxD, 4, {} }, { "y-scale", P_DOUBLE, 0, kMaxD, 4, {} },
         { "amount", P_DOUBLE, 0.0, 1.0, 1, {} }, { "turbulence", P_DOUBLE, 0.0, 1.0, 1, {} } }), false, 1 },
+    // videofiltersbad (gstvideofiltersbad.c:33-41); SURVEY 8f rank 4
+    { "zebrastripe", K_ZEBRASTRIPE, { "I420", "Y444", "Y42B", "Y41B", "YUY2", "UYVY", "AYUV", "NV12", "NV21", "YV12" },
+      { { "threshold", P_INT, 0, 100, 90, {}, false } }, false, 0 },           // gstzebrastripe.c:81-82,126-130
+    { "videodiff", K_VIDEODIFF, { "I420", "Y444", "Y42B", "Y41B" }, {}, false, 0 },                  // gstvideodiff.c:48-52
+    { "scenechange", K_SCENECHANGE, { "I420", "Y42B", "Y41B", "Y444" }, {}, false, 0 },              // gstscenechange.c:103-104
   };
   return f;
 }
@@ -153,6 +186,17 @@ struct b200vf_element {
   bool need_remap = true;
   int32_t *d_index = nullptr;
   size_t index_px = 0;
+  // videofiltersbad: luma geometry, zebrastripe's frame counter, the previous frame's luma plane (videodiff,
+  // scenechange keep a reference to the previous buffer: gstvideodiff.c:168-169, gstscenechange.c:193-194)
+  const YuvDef *yuv = nullptr;
+  int zebra_t = 0;
+  uint8_t *d_prev = nullptr;
+  size_t prev_bytes = 0;
+  bool have_prev = false;
+  uint32_t *d_sums = nullptr;
+  int sums_cap = 0;
+  b200vf_scenechange_state sc_state = { { 0, 0, 0, 0, 0 }, 0 };
+  std::vector<int> last_events;            // scenechange: per frame of the last transform, 1 = force-key-unit event pushed
   // host path: per-stream staging in HBM
   cudaStream_t hs[kHostStreams] = { nullptr, nullptr, nullptr };
   uint8_t *d_in[kHostStreams] = { nullptr, nullptr, nullptr };
@@ -291,6 +335,67 @@ int run (b200vf_element *e, const uint8_t *d_in, uint8_t *d_out, int nframes, cu
       return b200vf_chromahold (ctx, d_out, w, h, e->in_stride, e->in_bytes, nframes, e->fmt->off[0], e->fmt->off[1], e->fmt->off[2],
           (int) P["target-r"], (int) P["target-g"], (int) P["target-b"], (int) P["tolerance"], s);
     }
+    case K_ZEBRASTRIPE: {                                     // transform_frame_ip, gstzebrastripe.c:205-253
+      if (d_in != d_out) B200VF_CHECK_CUDA (cudaMemcpyAsync (d_out, d_in, e->in_bytes * nframes, cudaMemcpyDeviceToDevice, s));
+      const int t = e->zebra_t;
+      e->zebra_t += nframes;                                  // zebrastripe->t++ once per frame (:217)
+      return b200vf_zebrastripe (ctx, d_out + e->yuv->luma_off, e->yuv->luma_ps, e->in_stride, e->in_bytes, nframes, w, h,
+          b200vf_zebrastripe_y_threshold ((int) P["threshold"]), t, s);
+    }
+    case K_VIDEODIFF:
+    case K_SCENECHANGE: {
+      // Both compare the luma plane with the previous frame's. The reference keeps a reference to the previous
+      // GstBuffer; here the caller's buffers are its own, so the last frame's luma plane is copied aside (1 B/px).
+      const size_t luma_bytes = (size_t) e->in_stride * h;
+      if (e->prev_bytes != luma_bytes) {
+        if (e->d_prev) cudaFree (e->d_prev);
+        e->d_prev = nullptr; e->have_prev = false;
+        int rc = b200vf_malloc (ctx, luma_bytes, (void **) &e->d_prev);
+        if (rc) return rc;
+        e->prev_bytes = luma_bytes;
+      }
+      if (d_in != d_out) B200VF_CHECK_CUDA (cudaMemcpyAsync (d_out, d_in, e->in_bytes * nframes, cudaMemcpyDeviceToDevice, s));
+      // frame 0 against the saved plane (when there is one), frame f >= 1 against frame f-1 of this batch
+      const int first = e->have_prev ? 0 : 1;                 // the very first frame only passes through (:147-158 / :171-177)
+      int rc = B200VF_OK;
+      if (e->def->kind == K_VIDEODIFF) {                      // gst_video_diff_transform_frame, :131-173; threshold 10, t 0 (:89,98)
+        if (e->have_prev)
+          rc = b200vf_videodiff_luma (ctx, e->d_prev, e->in_stride, 0, d_in, e->in_stride, 0, d_out, e->in_stride, 0, w, h, 1, 10, 0, s);
+        if (!rc && nframes > 1)
+          rc = b200vf_videodiff_luma (ctx, d_in, e->in_stride, e->in_bytes, d_in + e->in_bytes, e->in_stride, e->in_bytes,
+              d_out + e->in_bytes, e->in_stride, e->in_bytes, w, h, nframes - 1, 10, 0, s);
+      } else {                                                // gst_scene_change_transform_frame_ip, :157-262
+        if (e->sums_cap < nframes) {
+          if (e->d_sums) cudaFree (e->d_sums);
+          e->d_sums = nullptr; e->sums_cap = 0;
+          rc = b200vf_malloc (ctx, sizeof (uint32_t) * (size_t) nframes, (void **) &e->d_sums);
+          if (rc) return rc;
+          e->sums_cap = nframes;
+        }
+        if (e->have_prev) rc = b200vf_sad_u8 (ctx, e->d_prev, e->in_stride, 0, d_in, e->in_stride, 0, w, h, 1, e->d_sums, s);
+        if (!rc && nframes > 1)
+          rc = b200vf_sad_u8 (ctx, d_in, e->in_stride, e->in_bytes, d_in + e->in_bytes, e->in_stride, e->in_bytes, w, h,
+              nframes - 1, e->d_sums + 1, s);
+        if (rc) return rc;
+        std::vector<uint32_t> sums ((size_t) nframes, 0u);
+        if (nframes - first > 0) {
+          B200VF_CHECK_CUDA (cudaMemcpyAsync (sums.data () + first, e->d_sums + first, sizeof (uint32_t) * (size_t) (nframes - first),
+              cudaMemcpyDeviceToHost, s));
+          B200VF_CHECK_CUDA (cudaStreamSynchronize (s));      // the decision is needed before transform_frame_ip returns
+        }
+        e->last_events.assign ((size_t) nframes, 0);
+        if (!e->have_prev) b200vf_scenechange_reset (&e->sc_state);          // :171-173
+        for (int f = first; f < nframes; f++) {
+          int change = 0;
+          b200vf_scenechange_update (&e->sc_state, ((double) sums[f]) / (w * h), &change);   // get_frame_score, :154
+          e->last_events[f] = change;
+        }
+      }
+      if (rc) return rc;
+      B200VF_CHECK_CUDA (cudaMemcpyAsync (e->d_prev, d_in + (size_t) (nframes - 1) * e->in_bytes, luma_bytes, cudaMemcpyDeviceToDevice, s));
+      e->have_prev = true;
+      return B200VF_OK;
+    }
     case K_GEOMETRIC: {
       if (e->need_remap || !e->d_index) {
         int rc = build_index (e, s);
@@ -331,6 +436,8 @@ B200VF_API void b200vf_element_destroy (b200vf_element *e) {
   free_staging (e);
   for (int i = 0; i < kHostStreams; i++) if (e->hs[i]) cudaStreamDestroy (e->hs[i]);
   if (e->d_index) cudaFree (e->d_index);
+  if (e->d_prev) cudaFree (e->d_prev);
+  if (e->d_sums) cudaFree (e->d_sums);
   delete e;
 }
 
@@ -412,6 +519,17 @@ B200VF_API int b200vf_element_set_caps (b200vf_element *e, const char *in_format
     e->in_bytes = (size_t) width * height * 4;
     e->out_stride = round_up_4 (width);
     e->out_bytes = (size_t) e->out_stride * height;
+  } else if (k == K_ZEBRASTRIPE || k == K_VIDEODIFF || k == K_SCENECHANGE) {        // planar / packed YUV, same format both sides
+    B200VF_REQUIRE (!strcmp (in_format, out_format), B200VF_E_UNSUPPORTED, "%s: cannot convert `%s` to `%s`", e->def->name, in_format, out_format);
+    B200VF_REQUIRE (in_template (in_format), B200VF_E_UNSUPPORTED, "%s: format `%s` is not in the pad template", e->def->name, in_format);
+    e->yuv = find_yuv (in_format);
+    B200VF_REQUIRE (e->yuv, B200VF_E_UNSUPPORTED, "%s: unknown format `%s`", e->def->name, in_format);
+    size_t size = 0;
+    yuv_geometry (in_format, width, height, &e->in_stride, &size);
+    e->out_stride = e->in_stride;
+    e->in_bytes = e->out_bytes = size;
+    e->fmt = nullptr;
+    e->have_prev = false;                                      // new caps: the saved frame no longer compares
   } else {                                                     // GstVideoFilter::set_info: same format both sides
     B200VF_REQUIRE (!strcmp (in_format, out_format), B200VF_E_UNSUPPORTED, "%s: cannot convert `%s` to `%s`", e->def->name, in_format, out_format);
     B200VF_REQUIRE (in_template (in_format), B200VF_E_UNSUPPORTED, "%s: format `%s` is not in the pad template", e->def->name, in_format);
@@ -457,16 +575,33 @@ B200VF_API int b200vf_element_transform_host (b200vf_element *e, const void *h_i
   // across frames (both copy engines + the SMs busy at once)
   const uint8_t *in = (const uint8_t *) h_in;
   uint8_t *out = (uint8_t *) h_out;
+  // (elements that compare with the previous frame, and zebrastripe's frame counter, need the frames in order)
+  const bool ordered = e->def->kind == K_ZEBRASTRIPE || e->def->kind == K_VIDEODIFF || e->def->kind == K_SCENECHANGE;
+  std::vector<int> events;
   for (int i = 0; i < nframes; i++) {
-    const int k = i % kHostStreams;
+    const int k = ordered ? 0 : i % kHostStreams;
     cudaStream_t s = e->hs[k];
     B200VF_CHECK_CUDA (cudaMemcpyAsync (e->d_in[k], in + (size_t) i * e->in_bytes, e->in_bytes, cudaMemcpyHostToDevice, s));
     rc = run (e, e->d_in[k], e->d_out[k], 1, s);
     if (rc) return rc;
     B200VF_CHECK_CUDA (cudaMemcpyAsync (out + (size_t) i * e->out_bytes, e->d_out[k], e->out_bytes, cudaMemcpyDeviceToHost, s));
+    if (ordered) {
+      B200VF_CHECK_CUDA (cudaStreamSynchronize (s));          // one staging buffer: it is reused by the next frame
+      if (e->def->kind == K_SCENECHANGE) events.push_back (e->last_events.empty () ? 0 : e->last_events[0]);
+    }
   }
   for (int k = 0; k < kHostStreams; k++) B200VF_CHECK_CUDA (cudaStreamSynchronize (e->hs[k]));
+  if (e->def->kind == K_SCENECHANGE) e->last_events = events;
   return B200VF_OK;
+}
+
+// scenechange: what the shell turns into force-key-unit events (gstscenechange.c:246-257). flags[i] = 1 when frame i
+// of the last transform call was detected as a scene change; returns the number of frames of that call (<0: status).
+B200VF_API int b200vf_element_last_events (const b200vf_element *e, int *flags, int capacity) {
+  B200VF_REQUIRE (e && (flags || capacity == 0) && capacity >= 0, B200VF_E_INVAL, "last_events: bad argument");
+  const int n = (int) e->last_events.size ();
+  for (int i = 0; i < n && i < capacity; i++) flags[i] = e->last_events[i];
+  return n;
 }
 
 // ------------------------------------------------------------ factory introspection
@@ -480,7 +615,7 @@ static int fill_info (const FactoryDef &f, b200vf_factory_info *out) {
       out->long_name = m.long_name; out->description = m.description; out->author = m.author;
     }
   B200VF_REQUIRE (out->plugin, B200VF_E_INVAL, "factory `%s` has no metadata row", f.name);
-  out->in_place = (f.kind == K_COLOREFFECTS || f.kind == K_CHROMAHOLD);
+  out->in_place = (f.kind == K_COLOREFFECTS || f.kind == K_CHROMAHOLD || f.kind == K_ZEBRASTRIPE || f.kind == K_SCENECHANGE);
   out->n_properties = (int) f.props.size ();
   out->n_formats = (int) f.formats.size ();
   return B200VF_OK;

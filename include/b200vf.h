@@ -357,6 +357,10 @@ int b200vf_element_transform_host (b200vf_element *e, const void *h_in, void *h_
 /* The same vfunc on device memory, asynchronous on `stream`. For in-place
  * elements d_out may equal d_in. */
 int b200vf_element_transform_device (b200vf_element *e, const void *d_in, void *d_out, int nframes, void *stream);
+/* scenechange only: flags[i] = 1 when frame i of the LAST transform call is a
+ * scene change, i.e. where the reference pushes its downstream force-key-unit
+ * event (gstscenechange.c:246-257). Returns the number of frames of that call. */
+int b200vf_element_last_events (const b200vf_element *e, int *flags, int capacity);
 
 /* ------------------------------------------------- factory introspection
  * What gst-inspect prints for each element, so that the C/GLib shells (gst/gstb200vf.c) can register the

@@ -58,6 +58,30 @@ def make_videofilters():
     print("golden_videofilters.npz: %d arrays" % len(g))
 
 
+def make_surface():
+    """element_surface.json from the reference's own API dump"""
+    cache = json.load(open(os.path.join(REF, "docs", "plugins", "gst_plugins_cache.json")))
+    want = {"bayer": ["bayer2rgb", "rgb2bayer"], "gaudieffects": None, "coloreffects": None, "geometrictransform": None,
+            "videofiltersbad": ["zebrastripe", "videodiff", "scenechange"]}
+    surf = {}
+    for plugin, only in want.items():
+        for name, el in cache[plugin]["elements"].items():
+            if only and name not in only:
+                continue
+            props = {}
+            for pn, pd in el.get("properties", {}).items():
+                if pn in ("name", "parent", "qos"):
+                    continue
+                props[pn] = {k: pd.get(k) for k in ("type", "min", "max", "default", "controllable") if k in pd}
+            pads = {pn: pd.get("caps") for pn, pd in el.get("pad-templates", {}).items()}
+            surf[name] = {"plugin": plugin, "klass": el.get("klass"), "hierarchy": el.get("hierarchy"), "properties": props,
+                          "pad-templates": pads, "long-name": el.get("long-name"), "description": el.get("description"),
+                          "author": el.get("author"), "rank": el.get("rank"),
+                          "plugin-description": cache[plugin].get("description"), "plugin-license": cache[plugin].get("license")}
+    json.dump(surf, open(os.path.join(HERE, "element_surface.json"), "w"), indent=1, sort_keys=True)
+    return surf
+
+
 def main():
     make_videofilters()
     R = oracle.get("reference")
@@ -128,30 +152,15 @@ def main():
     g["gt_out_fisheye_ayuv"] = R.remap(gsrc, g["gt_map_fisheye_0"] * 1.7 - 9.0, w, h, 4, "ignore", True)
     np.savez_compressed(os.path.join(HERE, "golden_small.npz"), **g)
 
-    # element surface from the reference's own API dump
-    cache = json.load(open(os.path.join(REF, "docs", "plugins", "gst_plugins_cache.json")))
-    want = {"bayer": ["bayer2rgb", "rgb2bayer"], "gaudieffects": None, "coloreffects": None, "geometrictransform": None}
-    surf = {}
-    for plugin, only in want.items():
-        for name, el in cache[plugin]["elements"].items():
-            if only and name not in only:
-                continue
-            props = {}
-            for pn, pd in el.get("properties", {}).items():
-                if pn in ("name", "parent", "qos"):
-                    continue
-                props[pn] = {k: pd.get(k) for k in ("type", "min", "max", "default", "controllable") if k in pd}
-            pads = {pn: pd.get("caps") for pn, pd in el.get("pad-templates", {}).items()}
-            surf[name] = {"plugin": plugin, "klass": el.get("klass"), "hierarchy": el.get("hierarchy"), "properties": props,
-                          "pad-templates": pads, "long-name": el.get("long-name"), "description": el.get("description"),
-                          "author": el.get("author"), "rank": el.get("rank"),
-                          "plugin-description": cache[plugin].get("description"), "plugin-license": cache[plugin].get("license")}
-    json.dump(surf, open(os.path.join(HERE, "element_surface.json"), "w"), indent=1, sort_keys=True)
+    surf = make_surface()
     print("wrote %d arrays, %d elements" % (len(g), len(surf)))
 
 
 if __name__ == "__main__" and "--videofilters" in sys.argv:
     make_videofilters()
+    sys.exit(0)
+if __name__ == "__main__" and "--surface" in sys.argv:
+    print("%d elements" % len(make_surface()))
     sys.exit(0)
 
 if __name__ == "__main__":

@@ -223,7 +223,7 @@ def test_element_surface_matches_reference_api_dump(vf):
             for f in fmts:
                 e.set_caps(f, f, 33, 17)
             with pytest.raises(vf.B200vfError):
-                e.set_caps("I420", "I420", 32, 16)
+                e.set_caps("v308", "v308", 32, 16)             # in no pad template of these plugins
         e.close()
 
 
@@ -246,7 +246,7 @@ def test_factory_introspection_matches_reference_api_dump(vf):
         assert f["plugin"] == e["plugin"] and f["type_name"] == e["hierarchy"][0] and f["parent_type_name"] == e["hierarchy"][1]
         assert f["klass"] == e["klass"] and f["long_name"] == e["long-name"] and f["description"] == e["description"]
         assert f["author"] == e["author"] and f["plugin_license"] == e["plugin-license"]
-        assert f["in_place"] == (1 if name in ("coloreffects", "chromahold") else 0)
+        assert f["in_place"] == (1 if name in ("coloreffects", "chromahold", "zebrastripe", "scenechange") else 0)   # transform_frame_ip
         props = {p["name"]: p for p in f["properties"]}
         for pn, pd in e["properties"].items():
             if pd["type"] == "GValueArray":
@@ -299,3 +299,39 @@ def test_packed_index_round_trips(vf):
     assert raw2 == raw + 1 and np.array_equal(vf.gt_unpack_index(packed2, w, h), idx)
     with pytest.raises(vf.B200vfError):
         vf.gt_unpack_index(packed2[:-8], w, h)           # truncated blob
+
+
+def test_yuv_frame_geometry_of_the_videofilters_elements(vf):
+    """default GstVideoInfo sizes (gst-plugins-base video-info.c fill_planes; external to the reference tree, so
+    written down here independently): pitches rounded up to 4, chroma planes per format"""
+    ru = lambda n, a: (n + a - 1) // a * a
+    def size(fmt, w, h):
+        s0, h2 = ru(w, 4), ru(h, 2)
+        if fmt in ("I420", "YV12"):
+            return s0 * h2 + 2 * ru(ru(w, 2) // 2, 4) * (h2 // 2)
+        if fmt == "Y444":
+            return 3 * s0 * h
+        if fmt == "Y42B":
+            return (s0 + ru(w, 8)) * h
+        if fmt == "Y41B":
+            return (s0 + ru(w, 16) // 2) * h
+        if fmt in ("NV12", "NV21"):
+            return s0 * h2 + s0 * (h2 // 2)
+        if fmt in ("YUY2", "UYVY"):
+            return ru(2 * w, 4) * h
+        return 4 * w * h
+    # known values (e.g. gst_video_info_set_format (I420, 320, 240) -> 115200; odd sizes round as above)
+    assert size("I420", 320, 240) == 115200 and size("NV12", 320, 240) == 115200 and size("Y42B", 320, 240) == 153600
+    assert size("Y41B", 320, 240) == 115200 and size("Y444", 320, 240) == 230400 and size("YUY2", 320, 240) == 153600
+    e = vf.Element(None, "zebrastripe")
+    for fmt in ["I420", "Y444", "Y42B", "Y41B", "YUY2", "UYVY", "AYUV", "NV12", "NV21", "YV12"]:
+        for (w, h) in [(320, 240), (33, 17), (7, 5), (1, 1)]:
+            e.set_caps(fmt, fmt, w, h)
+            assert e.unit_size() == (size(fmt, w, h), size(fmt, w, h)), (fmt, w, h)
+    assert e.get_property("threshold") == 90
+    e.close()
+    for name in ("videodiff", "scenechange"):
+        e = vf.Element(None, name)
+        with pytest.raises(vf.B200vfError):
+            e.set_caps("NV12", "NV12", 32, 16)                # planar Y formats only (gstvideodiff.c:48-52)
+        e.close()

@@ -116,3 +116,91 @@ def test_scenechange_scores_from_device_sads(ctx, vf, orc, rng):
     got = [st.update(x) for x in scores]
     assert got == orc.scenechange_run(scores)
     assert [i + 1 for i, c in enumerate(got) if c] == [17, 31]
+
+
+# ---------------------------------------------------------------- through the element mirror
+def _i420(rng, w, h, n):
+    ru = lambda v, a: (v + a - 1) // a * a
+    s0, h2 = ru(w, 4), ru(h, 2)
+    size = s0 * h2 + 2 * ru(ru(w, 2) // 2, 4) * (h2 // 2)
+    return rng.integers(0, 256, (n, size), dtype=np.uint8), s0
+
+
+def test_zebrastripe_element_i420_and_ayuv(ctx, orc, rng):
+    """element surface: `threshold` property, frame counter t across calls, chroma planes untouched"""
+    w, h, n = 70, 34, 3
+    fr, s0 = _i420(rng, w, h, n)
+    e = ctx.element("zebrastripe")
+    e.set_caps("I420", "I420", w, h)
+    e.set_property("threshold", 40)
+    for call in range(2):                                     # t keeps counting: frames 0..2, then 3..5
+        got = e.transform(fr, n).reshape(n, -1)
+        for f in range(n):
+            want = fr[f].copy()
+            want[: s0 * h] = orc.zebrastripe(fr[f][: s0 * h].reshape(h, s0), w, h, 40, call * n + f).reshape(-1)
+            assert np.array_equal(got[f], want), (call, f)
+    e.close()
+    ay = rng.integers(0, 256, (1, h, 4 * w), dtype=np.uint8)
+    e = ctx.element("zebrastripe")
+    e.set_caps("AYUV", "AYUV", w, h)
+    got = e.transform(ay, 1).reshape(h, 4 * w)
+    assert np.array_equal(got, orc.zebrastripe(ay[0], w, h, 90, 0, 4, 1))
+    e.close()
+
+
+def test_videodiff_element_sequence(ctx, orc, rng):
+    """first frame passes through, every later one is compared with its predecessor - across a device batch and
+    across calls (host path, one frame per call)"""
+    w, h, n = 66, 30, 5
+    fr, s0 = _i420(rng, w, h, n)
+    for f in range(1, n):                                     # luma drifts a little, with a few big changes
+        y = fr[f - 1][: s0 * h].astype(int) + rng.integers(-12, 13, s0 * h)
+        fr[f][: s0 * h] = y.clip(0, 255).astype(np.uint8)
+    want = fr.copy()
+    for f in range(1, n):
+        want[f][: s0 * h] = orc.videodiff_luma(fr[f - 1][: s0 * h].reshape(h, s0), fr[f][: s0 * h].reshape(h, s0), w, h, 10, 0).reshape(-1)
+    # rows of the luma plane beyond `w` are padding: the reference loop never writes them, the kernel works on the
+    # pixels only, the rest of the plane is the copy of the input
+    e = ctx.element("videodiff")
+    e.set_caps("I420", "I420", w, h)
+    d_in, d_out = ctx.upload(fr), ctx.alloc(fr.size)
+    e.transform_device(d_in, d_out, n)                        # one batch
+    got = ctx.download(d_out, fr.size).reshape(n, -1)
+    luma = lambda a: a[:, : s0 * h].reshape(len(a), h, s0)[:, :, :w]
+    assert np.array_equal(luma(got), luma(want)) and np.array_equal(got[:, s0 * h:], fr[:, s0 * h:])
+    e.close()
+    e = ctx.element("videodiff")
+    e.set_caps("I420", "I420", w, h)
+    got2 = np.stack([e.transform(fr[f], 1) for f in range(n)])    # frame by frame through the host path
+    assert np.array_equal(luma(got2), luma(want)) and np.array_equal(got2[:, s0 * h:], fr[:, s0 * h:])
+    e.close()
+
+
+def test_scenechange_element_events(ctx, vf, orc, rng):
+    w, h, n = 160, 90, 30
+    clip, s0 = _i420(rng, w, h, n)
+    base = clip[0][: s0 * h].copy()
+    for f in range(n):
+        if f in (12, 21):
+            base = rng.integers(0, 256, s0 * h, dtype=np.uint8)
+        base = (base.astype(int) + rng.integers(-3, 4, s0 * h)).clip(0, 255).astype(np.uint8)
+        clip[f][: s0 * h] = base
+    scores = [orc.sad_u8(clip[f][: s0 * h].reshape(h, s0), clip[f + 1][: s0 * h].reshape(h, s0), w, h) / (w * h) for f in range(n - 1)]
+    want = [False] + orc.scenechange_run(scores)              # frame 0 only primes the element
+    e = ctx.element("scenechange")
+    e.set_caps("I420", "I420", w, h)
+    d = ctx.upload(clip)
+    e.transform_device(d, d, 10)                              # in place, three batches: state carries over
+    ev = e.last_events()
+    e.transform_device(d.ptr + 10 * clip.shape[1], d.ptr + 10 * clip.shape[1], 13)
+    ev += e.last_events()
+    e.transform_device(d.ptr + 23 * clip.shape[1], d.ptr + 23 * clip.shape[1], 7)
+    ev += e.last_events()
+    assert ev == want and [i for i, c in enumerate(ev) if c] == [12, 21]
+    assert np.array_equal(ctx.download(d, clip.size).reshape(clip.shape), clip)      # passthrough
+    e.close()
+    e = ctx.element("scenechange")
+    e.set_caps("I420", "I420", w, h)
+    out = e.transform(clip, n)                                # host path, frame by frame
+    assert e.last_events() == want and np.array_equal(out.reshape(clip.shape), clip)
+    e.close()
