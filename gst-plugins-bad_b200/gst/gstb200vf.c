@@ -1,8 +1,9 @@
 /* gstb200vf.c - GStreamer element shells over libb200vf.so (C/GLib, no per-pixel work).
  *
- * One source, compiled once per plugin with -DB200VF_PLUGIN=<bayer|gaudieffects|coloreffects|geometrictransform>
- * (gst/meson.build), yields libgstbayer.so, libgstgaudieffects.so, libgstcoloreffects.so and
- * libgstgeometrictransform.so that REPLACE the stock plugins: same plugin names, factory names, GType names and
+ * One source, compiled once per plugin with
+ * -DB200VF_PLUGIN=<bayer|gaudieffects|coloreffects|geometrictransform|videofiltersbad>
+ * (gst/meson.build), yields libgstbayer.so, libgstgaudieffects.so, libgstcoloreffects.so,
+ * libgstgeometrictransform.so and libgstvideofiltersbad.so (zebrastripe, videodiff, scenechange) that REPLACE the stock plugins: same plugin names, factory names, GType names and
  * parents, klass/description strings, GObject properties (names, ranges, defaults, GST_PARAM_CONTROLLABLE) and pad
  * templates - all taken from the introspection table of the library (b200vf_factory_*), which is generated from and
  * tested against the reference's own API dump (docs/plugins/gst_plugins_cache.json). The data vfuncs
@@ -26,7 +27,7 @@
 #include "b200vf.h"
 
 #ifndef B200VF_PLUGIN
-#error "compile with -DB200VF_PLUGIN=bayer|gaudieffects|coloreffects|geometrictransform"
+#error "compile with -DB200VF_PLUGIN=bayer|gaudieffects|coloreffects|geometrictransform|videofiltersbad"
 #endif
 #define STR_(x) #x
 #define STR(x) STR_(x)
@@ -46,6 +47,7 @@ typedef struct
   b200vf_ctx *ctx;
   b200vf_element *el;
   gint device;
+  guint key_unit_count;         /* scenechange: running count of the force-key-unit events (gstscenechange.c:255) */
 } GstB200vf;
 
 typedef struct
@@ -235,11 +237,24 @@ b200vf_transform_frame (GstVideoFilter * vf, GstVideoFrame * in, GstVideoFrame *
           GST_VIDEO_FRAME_PLANE_DATA (in, 0), GST_VIDEO_FRAME_PLANE_DATA (out, 0), 1));
 }
 
+/* (planar YUV frames of the videofiltersbad elements: the planes of a default-layout GstVideoInfo are contiguous
+ * from plane 0, which is the layout the element mirror computes; a buffer with a GstVideoMeta that moves planes
+ * would be copied into that layout first - not needed for videotestsrc / decoders' default pools) */
 static GstFlowReturn
 b200vf_transform_frame_ip (GstVideoFilter * vf, GstVideoFrame * frame)
 {
+  GstB200vf *self = B200VF (vf);
   guint8 *d = GST_VIDEO_FRAME_PLANE_DATA (frame, 0);
-  return b200vf_flow (B200VF (vf), b200vf_element_transform_host (B200VF (vf)->el, d, d, 1));
+  GstFlowReturn ret = b200vf_flow (self, b200vf_element_transform_host (self->el, d, d, 1));
+  /* scenechange: the detection becomes a downstream force-key-unit event (gstscenechange.c:246-257) */
+  if (ret == GST_FLOW_OK && !strcmp (B200VF_GET_CLASS (self)->factory, "scenechange")) {
+    int changed = 0;
+    if (b200vf_element_last_events (self->el, &changed, 1) == 1 && changed)
+      gst_pad_push_event (GST_BASE_TRANSFORM_SRC_PAD (self),
+          gst_video_event_new_downstream_force_key_unit (GST_BUFFER_PTS (frame->buffer), GST_CLOCK_TIME_NONE,
+              GST_CLOCK_TIME_NONE, FALSE, self->key_unit_count++));
+  }
+  return ret;
 }
 
 static GstFlowReturn
