@@ -83,6 +83,18 @@ def test_aligned_view_equals_prepass_route_and_oracle(ctx, vf, orc, rng, monkeyp
         assert np.array_equal(got2, want), ("pre-pass", sigma, np.argwhere(got2 != want)[:6])
 
 
+@pytest.mark.parametrize("p0", [0, 1])
+def test_widest_window_on_the_tiled_path(ctx, vf, orc, rng, p0):
+    """|sigma| = 20: 101 taps, halo of 100 rows > the 64-row step (carried rows move in two batches), 158 KB of
+    shared memory (one CTA per SM); sigma = -20 takes the IEEE-division / clamping epilogue (negative taps)"""
+    w, h = 160, 140
+    fr = frames.random_u8(rng, h, 4 * w)
+    for sigma in (20, -20):
+        got = run(ctx, vf, fr, w, h, sigma, p0)
+        want = orc.gaussblur(fr, w, h, sigma, p0)
+        assert np.array_equal(got, want), (sigma, p0, ctx.last_kernel(), np.argwhere(got != want)[:6])
+
+
 def test_final_rounding_all_fp32(ctx):
     """(guint8) CLAMP (q + 0.5 [fp64], 0, 255) computed without fp64 (finish_bits / finish_u8): every fp32 q"""
     assert ctx.gauss_selftest_finish(0, 0xffffffff) == 0

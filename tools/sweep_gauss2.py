@@ -1,5 +1,5 @@
 """gaussblur timing over the library's tuning knobs in ONE process (run under gpurun).
-   python tools/sweep_gauss2.py "NT=256,GTH=64" "NT=128,GTH=32" ...   (knob = B200VF_GAUSS_<name>)"""
+   python tools/sweep_gauss2.py "" "GTH=96" "CTAS=148" "EDGEW=4" "PREPASS=1" ...   (knob = B200VF_GAUSS_<name>)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gst-plugins-bad_b200"))
