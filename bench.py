@@ -414,6 +414,10 @@ def side_measurements(ctx, torch, b200vf, st, side, peak):
         rec("videodiff_luma_%s" % tag, n, px, 3, t)
         t = timeit(lambda: ctx.zebrastripe(src2, 1, w, w, h, threshold=90, nframes=n, stream=st))
         rec("zebrastripe_%s" % tag, n, px, 2, t)
+        # smooth (gst/smooth): adaptive 7x9 box filter, bound by integer issue (63 compares per sample), not by HBM
+        ns = min(n, 8)
+        t = timeit(lambda: ctx.smooth_plane(src, lum_out, w, w, h, nframes=ns, stream=st), iters=3)
+        rec("smooth_luma_%s" % tag, ns, px, 2, t, {"bound": "integer issue: (2fs+1)(2fs+3) = 63 compares per sample at filter-size 3"})
         del src2, lum_out, sums
         del src
         # 4-byte -> 4-byte elements on the RGBA batch

@@ -89,6 +89,7 @@ _SIGS = {
     "b200vf_zebrastripe": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _i, _i, _i, _vp]),
     "b200vf_videodiff_luma": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _vp]),
     "b200vf_sad_u8": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _vp, _vp]),
+    "b200vf_smooth_plane": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _vp]),
     "b200vf_scenechange_reset": (_i, [_vp]),
     "b200vf_scenechange_update": (_i, [_vp, C.c_double, C.POINTER(_i)]),
     "b200vf_bayer2rgb_fused": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -297,6 +298,11 @@ class Context:
     def sad_u8(self, a, b, stride, width, height, sums, nframes=1, frame_stride=None, stream=None):
         fs = frame_stride if frame_stride is not None else stride * height
         check(lib.b200vf_sad_u8(self.h, _ptr(a), stride, fs, _ptr(b), stride, fs, width, height, nframes, _ptr(sums), stream))
+
+    def smooth_plane(self, src, dst, stride, width, height, tolerance=8, filtersize=3, nframes=1, frame_stride=None, stream=None):
+        fs = frame_stride if frame_stride is not None else stride * height
+        check(lib.b200vf_smooth_plane(self.h, _ptr(src), stride, fs, _ptr(dst), stride, fs, width, height, nframes,
+                                      tolerance, filtersize, stream))
 
     def gauss_selftest_finish(self, lo_bits=0, hi_bits=0xffffffff):
         """mismatches between the blur's fp32-only final rounding and (guint8) CLAMP (q + 0.5 [fp64], 0, 255)"""

@@ -225,6 +225,64 @@ sad_kernel (const uint8_t *a, int a_stride, size_t a_fs, const uint8_t *b, int b
   }
 }
 
+// ---- smooth (gst/smooth/gstsmooth.c:131-176, its own plugin; same boundary, I420 planes) -----------------
+// Adaptive box filter: the output is the mean of the window samples within +-tolerance of the reference sample
+// (plus the reference sample itself, counted once more), integer division. The reference's loop has two
+// quirks this kernel reproduces (smooth_geometry): the row pointers are advanced at the END of an iteration to
+// row y, so iteration y reads its reference sample from row y-1 and writes row y-1 with the window of row y -
+// output row r is computed with rows [max(0, r-fs), r+fs+3) (clipped as the loop clips them), row 0 is written
+// twice (the second time wins) and the LAST row is never written; the columns are the symmetric [x-fs, x+fs].
+// Unlike the other filters here this one is bound by integer issue, not by HBM: (2fs+1)(2fs+3) = 63 compares
+// per sample at the default filter-size 3.
+constexpr int SM_TW = 64, SM_TH = 16, SM_FS_MAX = 8;
+
+// window rows [ra, rb) of loop iteration y (fy1 / fy2 of the reference divided by the stride)
+__host__ __device__ inline void smooth_rows (int y, int height, int fs, int *ra, int *rb) {
+  const int a = y - (fs + 1);
+  *ra = a > 0 ? a : 0;
+  const int lim = height - (fs + 1) > 0 ? height - (fs + 1) : 0;
+  *rb = (fs + 1 < height ? fs + 1 : height) + (y + 1 < lim ? y + 1 : lim);
+}
+
+__global__ void __launch_bounds__ (256)
+smooth_kernel (const uint8_t *src, int src_stride, size_t src_fs, uint8_t *dst, int dst_stride, size_t dst_fs,
+    int width, int height, int atol, int fs /* >= 0 */, int empty_window)
+{
+  __shared__ uint8_t tile[SM_TH + 2 * SM_FS_MAX + 2][SM_TW + 2 * SM_FS_MAX];
+  const uint8_t *s = src + (size_t) blockIdx.z * src_fs;
+  uint8_t *d = dst + (size_t) blockIdx.z * dst_fs;
+  const int x0 = blockIdx.x * SM_TW, r0 = blockIdx.y * SM_TH;
+  const int tid = threadIdx.y * 64 + threadIdx.x;
+  const int trows = SM_TH + 2 * fs + 2, tcols = SM_TW + 2 * fs;
+  for (int i = tid; i < trows * tcols; i += 256) {           // rows r0-fs .. r0+TH+fs+1, columns x0-fs .. x0+TW+fs-1
+    const int tr = i / tcols, tc = i % tcols;
+    const int gr = r0 - fs + tr, gc = x0 - fs + tc;
+    tile[tr][tc] = (gr >= 0 && gr < height && gc >= 0 && gc < width) ? s[(size_t) gr * src_stride + gc] : (uint8_t) 0;
+  }
+  __syncthreads ();
+  const int x = x0 + threadIdx.x;
+  const int last = height >= 2 ? height - 2 : 0;             // last row the reference writes
+  if (x >= width) return;
+  const int c0 = max (x - fs, 0), c1 = empty_window ? c0 : min (x + fs + 1, width);
+#pragma unroll 1
+  for (int k = 0; k < SM_TH / 4; k++) {
+    const int r = r0 + threadIdx.y * (SM_TH / 4) + k;
+    if (r > last) break;
+    int ra, rb;
+    smooth_rows (height >= 2 ? r + 1 : 0, height, fs, &ra, &rb);
+    const int ref = tile[r - r0 + fs][x - x0 + fs];
+    int num = 1, sum = ref;
+    for (int wr = ra; wr < rb; wr++) {
+      const uint8_t *row = tile[wr - r0 + fs] + (fs - x0);
+      for (int wc = c0; wc < c1; wc++) {
+        const int akt = row[wc];
+        if (abs (akt - ref) < atol) { num++; sum += akt; }
+      }
+    }
+    d[(size_t) r * dst_stride + x] = (uint8_t) (sum / num);
+  }
+}
+
 bool aligned16 (const void *p, size_t a, size_t b) { return ((uintptr_t) p) % 16 == 0 && a % 16 == 0 && b % 16 == 0; }
 bool aligned4 (const void *p, size_t a, size_t b) { return ((uintptr_t) p) % 4 == 0 && a % 4 == 0 && b % 4 == 0; }
 
@@ -304,6 +362,29 @@ B200VF_API int b200vf_sad_u8 (b200vf_ctx *ctx, const uint8_t *d_a, int a_stride,
     sad_kernel<1><<<vf_grid (width, height, nframes, 1), block, 0, s>>> (d_a, a_stride, a_frame_stride, d_b, b_stride, b_frame_stride,
         width, height, d_sums);
   return b200vf_launched (ctx, "sad_u8");
+}
+
+// smooth_filter on one plane (luma, or a chroma plane when luma-only is off). Rows 0 .. height-2 of the
+// destination are written (row 0 only, for a one-row plane); the last row keeps what the buffer held, as in the
+// reference. (lower - akt) * (upper - akt) < 0 is |akt - ref| < |tolerance| for every tolerance that does not
+// overflow the reference's int product; |tolerance| > 255 admits every sample.
+B200VF_API int b200vf_smooth_plane (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
+    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int height, int nframes, int tolerance,
+    int filtersize, void *stream)
+{
+  B200VF_REQUIRE (ctx && d_src && d_dst && width > 0 && height > 0 && nframes > 0, B200VF_E_INVAL, "smooth: bad argument");
+  B200VF_REQUIRE (src_stride >= width && dst_stride >= width, B200VF_E_INVAL, "smooth: row stride");
+  B200VF_REQUIRE (filtersize <= SM_FS_MAX, B200VF_E_UNSUPPORTED, "smooth: filter-size %d (supported: <= %d)", filtersize, SM_FS_MAX);
+  B200VF_REQUIRE ((height + SM_TH - 1) / SM_TH <= 65535 && nframes <= 65535, B200VF_E_UNSUPPORTED, "smooth: grid limits");
+  cudaStream_t s = b200vf_stream (ctx, stream);
+  long long at = tolerance < 0 ? -(long long) tolerance : (long long) tolerance;
+  const int atol = at > 256 ? 256 : (int) at;
+  // a negative filter-size leaves the window empty (fx1 >= fx2 in the reference's loop): the output is the reference sample
+  const int fs = filtersize < 0 ? 0 : filtersize;
+  const dim3 block (64, 4), grid ((width + SM_TW - 1) / SM_TW, (height + SM_TH - 1) / SM_TH, nframes);
+  smooth_kernel<<<grid, block, 0, s>>> (d_src, src_stride, src_frame_stride, d_dst, dst_stride, dst_frame_stride, width, height, atol, fs,
+      filtersize < 0 ? 1 : 0);
+  return b200vf_launched (ctx, "smooth");
 }
 
 // gst_scene_change_transform_frame_ip, gstscenechange.c:196-236: the decision on the frame score

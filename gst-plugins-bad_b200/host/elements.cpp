@@ -22,7 +22,7 @@
 namespace {
 
 enum Kind { K_BAYER2RGB, K_RGB2BAYER, K_BURN, K_CHROMIUM, K_DILATE, K_DODGE, K_EXCLUSION, K_GAUSSBLUR, K_SOLARIZE,
-  K_COLOREFFECTS, K_CHROMAHOLD, K_GEOMETRIC, K_ZEBRASTRIPE, K_VIDEODIFF, K_SCENECHANGE };
+  K_COLOREFFECTS, K_CHROMAHOLD, K_GEOMETRIC, K_ZEBRASTRIPE, K_VIDEODIFF, K_SCENECHANGE, K_SMOOTH };
 
 struct FormatDef { const char *name; int pstride; int off[4]; /* R,G,B,A (or Y,U,V,A) poffsets; -1 = none */ };
 // gst-plugins-base video-format.c packed layouts (byte offsets in memory)
@@ -158,6 +158,9 @@ const std::vector<FactoryDef> &factories () {
       { { "threshold", P_INT, 0, 100, 90, {}, false } }, false, 0 },           // gstzebrastripe.c:81-82,126-130
     { "videodiff", K_VIDEODIFF, { "I420", "Y444", "Y42B", "Y41B" }, {}, false, 0 },                  // gstvideodiff.c:48-52
     { "scenechange", K_SCENECHANGE, { "I420", "Y42B", "Y41B", "Y444" }, {}, false, 0 },              // gstscenechange.c:103-104
+    // smooth (gst/smooth/gstsmooth.c:40-54,76-89; instance defaults :121-126)
+    { "smooth", K_SMOOTH, { "I420" }, { { "active", P_BOOL, 0, 1, 1, {}, false }, { "tolerance", P_INT, -2147483648.0, 2147483647.0, 8, {}, false },
+        { "filter-size", P_INT, -2147483648.0, 2147483647.0, 3, {}, false }, { "luma-only", P_BOOL, 0, 1, 1, {}, false } }, false, 0 },
   };
   return f;
 }
@@ -396,6 +399,27 @@ int run (b200vf_element *e, const uint8_t *d_in, uint8_t *d_out, int nframes, cu
       e->have_prev = true;
       return B200VF_OK;
     }
+    case K_SMOOTH: {                                          // gst_smooth_transform_frame, gstsmooth.c:178-222 (I420)
+      if (P["active"] == 0) {
+        if (d_in != d_out) B200VF_CHECK_CUDA (cudaMemcpyAsync (d_out, d_in, e->in_bytes * nframes, cudaMemcpyDeviceToDevice, s));
+        return B200VF_OK;
+      }
+      B200VF_REQUIRE (d_in != d_out, B200VF_E_INVAL, "smooth: transform_frame needs distinct input and output buffers");
+      const int tol = (int) P["tolerance"], fs = (int) P["filter-size"];
+      const int s0 = e->in_stride, h2 = round_up (h, 2);
+      const int cw = round_up (w, 2) / 2, ch = h2 / 2, s1 = round_up (cw, 4);
+      const size_t off1 = (size_t) s0 * h2, off2 = off1 + (size_t) s1 * ch;
+      int rc = b200vf_smooth_plane (ctx, d_in, s0, e->in_bytes, d_out, s0, e->in_bytes, w, h, nframes, tol, fs, s);
+      if (rc) return rc;
+      if (P["luma-only"] != 0) {                              // gst_video_frame_copy_plane (1), (2): one strided copy per batch
+        B200VF_CHECK_CUDA (cudaMemcpy2DAsync (d_out + off1, e->in_bytes, d_in + off1, e->in_bytes, e->in_bytes - off1, nframes,
+            cudaMemcpyDeviceToDevice, s));
+        return B200VF_OK;
+      }
+      rc = b200vf_smooth_plane (ctx, d_in + off1, s1, e->in_bytes, d_out + off1, s1, e->in_bytes, cw, ch, nframes, tol, fs, s);
+      if (rc) return rc;
+      return b200vf_smooth_plane (ctx, d_in + off2, s1, e->in_bytes, d_out + off2, s1, e->in_bytes, cw, ch, nframes, tol, fs, s);
+    }
     case K_GEOMETRIC: {
       if (e->need_remap || !e->d_index) {
         int rc = build_index (e, s);
@@ -519,7 +543,7 @@ B200VF_API int b200vf_element_set_caps (b200vf_element *e, const char *in_format
     e->in_bytes = (size_t) width * height * 4;
     e->out_stride = round_up_4 (width);
     e->out_bytes = (size_t) e->out_stride * height;
-  } else if (k == K_ZEBRASTRIPE || k == K_VIDEODIFF || k == K_SCENECHANGE) {        // planar / packed YUV, same format both sides
+  } else if (k == K_ZEBRASTRIPE || k == K_VIDEODIFF || k == K_SCENECHANGE || k == K_SMOOTH) {   // planar / packed YUV, same format both sides
     B200VF_REQUIRE (!strcmp (in_format, out_format), B200VF_E_UNSUPPORTED, "%s: cannot convert `%s` to `%s`", e->def->name, in_format, out_format);
     B200VF_REQUIRE (in_template (in_format), B200VF_E_UNSUPPORTED, "%s: format `%s` is not in the pad template", e->def->name, in_format);
     e->yuv = find_yuv (in_format);

@@ -285,6 +285,22 @@ typedef struct b200vf_scenechange_state { double diffs[B200VF_SC_N_DIFFS]; int n
 int b200vf_scenechange_reset (b200vf_scenechange_state *st);
 int b200vf_scenechange_update (b200vf_scenechange_state *st, double score, int *change_out);
 
+/* ------------------------------------------------------------ smooth plugin
+ * smooth_filter (gst/smooth/gstsmooth.c:131-176) on one 8-bit plane: the mean
+ * (integer division) of the reference sample and of the window samples within
+ * +-tolerance of it. Window: columns [x-fs, x+fs], rows [r-fs, r+fs+2] around
+ * output row r (the reference reads its reference sample one row above the
+ * window centre), clipped as the reference's loop clips them. Rows 0 ..
+ * height-2 are written; the last row is never written by the reference and is
+ * left untouched here. filtersize <= 8 (negative: empty window, output =
+ * input); any tolerance (the reference's int product overflows - undefined -
+ * beyond |tolerance| ~ 46000; here every |tolerance| > 255 admits all samples). The element (`active`, `tolerance` 8, `filter-size` 3,
+ * `luma-only` TRUE; I420) filters plane 0 and copies or filters planes 1, 2
+ * (:178-222). */
+int b200vf_smooth_plane (b200vf_ctx *ctx, const uint8_t *d_src, int src_stride, size_t src_frame_stride,
+    uint8_t *d_dst, int dst_stride, size_t dst_frame_stride, int width, int height, int nframes, int tolerance,
+    int filtersize, void *stream);
+
 /* ------------------------------------------------------------ fused chains
  * bayer2rgb followed by per-channel LUT elements (coloreffects per-channel
  * presets, burn, dodge, chromium, solarize, composed on the host) and/or one

@@ -468,6 +468,17 @@ TUS["ref_scenechange.c"] = lambda: (
     + "  }\n  return change;\n}\n")
 
 
+TUS["ref_smooth.c"] = lambda: (
+    "#include <glib.h>\n"
+    + func("gst/smooth/gstsmooth.c", "smooth_filter")
+    + """
+void ref_smooth_plane (guchar *dest, guchar *src, int width, int height, int stride, int dstride, int tolerance, int filtersize)
+{
+  smooth_filter (dest, src, width, height, stride, dstride, tolerance, filtersize);
+}
+""")
+
+
 def register_gt_tus():
     for name in GT_ELEMENTS:
         TUS["ref_gt_%s.c" % name] = gt_tu(name)

@@ -218,6 +218,13 @@ class Port(_Base):
         self.lib.oracle_sad_u8.restype = C.c_uint32
         return int(self.lib.oracle_sad_u8(_p(a), a.shape[1], _p(b), b.shape[1], width, height))
 
+    def smooth_plane(self, plane, width, height, tolerance=8, filtersize=3, prefill=0):
+        """returns the filtered plane; rows the reference never writes keep `prefill`"""
+        plane = _u8(plane)
+        out = np.full_like(plane, prefill)
+        self.lib.oracle_smooth_plane(_p(out), _p(plane), width, height, plane.shape[1], plane.shape[1], tolerance, filtersize)
+        return out
+
     def scenechange_run(self, scores):
         """the element's decision over a sequence of frame scores -> list of bools"""
         class S(C.Structure):
@@ -396,6 +403,12 @@ class Ref(_Base):
         self.lib.ref_scenechange_score.restype = C.c_double
         self.lib.ref_scenechange_score(_p(a), a.shape[1], _p(b), b.shape[1], width, height, C.byref(sad))
         return int(sad.value)
+
+    def smooth_plane(self, plane, width, height, tolerance=8, filtersize=3, prefill=0):
+        plane = _u8(plane)
+        out = np.full_like(plane, prefill)
+        self.lib.ref_smooth_plane(_p(out), _p(plane), width, height, plane.shape[1], plane.shape[1], tolerance, filtersize)
+        return out
 
     def scenechange_run(self, scores):
         class S(C.Structure):

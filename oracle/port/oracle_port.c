@@ -574,3 +574,33 @@ oracle_scenechange_update (oracle_scenechange *sc, double score)
   if (change) { memset (sc->diffs, 0, sizeof sc->diffs); sc->n_diffs = 0; }
   return change;
 }
+
+/* smooth: gst/smooth/gstsmooth.c:131-176 in closed form. Iteration y of the reference
+ * reads its reference sample from row max(y-1,0) and writes that row, with window rows
+ * [max(0,y-fs-1), min(fs+1,h) + min(y+1, max(0,h-fs-1))); row 0 is written twice (the
+ * later iteration wins), the last row never. */
+EXPORT void
+oracle_smooth_plane (uint8_t *dest, const uint8_t *src, int width, int height, int stride, int dstride,
+    int tolerance, int filtersize)
+{
+  int fs = filtersize;
+  for (int y = 0; y < height; y++) {
+    int r = y > 0 ? y - 1 : 0;
+    long long ra = (long long) y - ((long long) fs + 1); if (ra < 0) ra = 0;
+    long long lim = (long long) height - ((long long) fs + 1); if (lim < 0) lim = 0;
+    long long rb = ((long long) fs + 1 < height ? (long long) fs + 1 : height) + (y + 1 < lim ? y + 1 : lim);
+    for (int x = 0; x < width; x++) {
+      int ref = src[(size_t) r * stride + x];
+      int upper = ref + tolerance, lower = ref - tolerance;
+      int num = 1, sum = ref;
+      long long c0 = (long long) x - fs; if (c0 < 0) c0 = 0;
+      long long c1 = (long long) x + fs + 1; if (c1 > width) c1 = width;
+      for (long long wr = ra; wr < rb; wr++)
+        for (long long wc = c0; wc < c1; wc++) {
+          int akt = src[(size_t) wr * stride + wc];
+          if ((lower - akt) * (upper - akt) < 0) { num++; sum += akt; }
+        }
+      dest[(size_t) r * dstride + x] = (uint8_t) (sum / num);
+    }
+  }
+}

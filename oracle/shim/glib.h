@@ -22,6 +22,7 @@ typedef int gboolean;
 typedef float gfloat;
 typedef double gdouble;
 typedef char gchar;
+typedef unsigned char guchar;
 typedef size_t gsize;
 typedef void *gpointer;
 #ifndef TRUE

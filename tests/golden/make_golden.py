@@ -52,6 +52,11 @@ def make_videofilters():
     g["sad"] = np.array([R.sad_u8(a, b, w, h)], np.uint32)
     scores = np.concatenate([rng.uniform(0, 8, 30), [70.0], rng.uniform(0, 8, 8), [33.0, 2, 2, 2, 2, 2, 90, 100],
                              rng.uniform(20, 60, 20)])
+    # smooth (its own plugin): plateaus + noise so that the tolerance matters; rows never written keep the prefill 77
+    sm = ((rng.integers(0, 256, (h, st)) // 32) * 32 + rng.integers(0, 12, (h, st))).astype(np.uint8)
+    g["smooth_src"] = sm
+    for tol, fs in [(8, 3), (0, 3), (-5, 2), (300, 1), (8, 0), (8, -1), (20, 8)]:
+        g["smooth_%d_%d" % (tol, fs)] = R.smooth_plane(sm, w, h, tol, fs, 77)
     g["sc_scores"] = scores
     g["sc_changes"] = np.array(R.scenechange_run(scores), np.uint8)
     np.savez_compressed(os.path.join(HERE, "golden_videofilters.npz"), **g)
@@ -62,7 +67,7 @@ def make_surface():
     """element_surface.json from the reference's own API dump"""
     cache = json.load(open(os.path.join(REF, "docs", "plugins", "gst_plugins_cache.json")))
     want = {"bayer": ["bayer2rgb", "rgb2bayer"], "gaudieffects": None, "coloreffects": None, "geometrictransform": None,
-            "videofiltersbad": ["zebrastripe", "videodiff", "scenechange"]}
+            "videofiltersbad": ["zebrastripe", "videodiff", "scenechange"], "smooth": None}
     surf = {}
     for plugin, only in want.items():
         for name, el in cache[plugin]["elements"].items():

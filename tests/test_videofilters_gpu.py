@@ -204,3 +204,54 @@ def test_scenechange_element_events(ctx, vf, orc, rng):
     out = e.transform(clip, n)                                # host path, frame by frame
     assert e.last_events() == want and np.array_equal(out.reshape(clip.shape), clip)
     e.close()
+
+
+# ---------------------------------------------------------------- smooth (gst/smooth)
+def _plateaus(rng, h, st):
+    return ((rng.integers(0, 256, (h, st)) // 32) * 32 + rng.integers(0, 12, (h, st))).astype(np.uint8)
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (1, 5), (5, 1), (4, 2), (22, 13), (70, 40), (130, 37), (642, 50)])
+def test_smooth_plane(ctx, orc, rng, w, h):
+    """smooth_filter incl. its quirks: reference sample one row above the window centre, asymmetric rows, row 0
+    written twice, last row never written (it keeps what the destination held: 77 here)"""
+    st = frames.round_up_4(w)
+    src = _plateaus(rng, h, st)
+    for tol, fs in [(8, 3), (0, 3), (1, 1), (-5, 2), (300, 1), (8, 0), (8, -1), (20, 8), (-40000, 2)]:      # beyond |tolerance| ~ 46000 the reference's int product overflows (undefined)
+        d_dst = up(ctx, np.full((h, st), 77, np.uint8))
+        ctx.smooth_plane(up(ctx, src), d_dst, st, w, h, tolerance=tol, filtersize=fs)
+        got = ctx.download(d_dst, h * st).reshape(h, st)
+        want = orc.smooth_plane(src, w, h, tol, fs, 77)
+        assert np.array_equal(got[:, :w], want[:, :w]), (w, h, tol, fs, np.argwhere(got[:, :w] != want[:, :w])[:4])
+        assert (got[:, w:] == 77).all()                      # padding columns are not touched
+    with pytest.raises(Exception):
+        ctx.smooth_plane(up(ctx, src), up(ctx, src), st, w, h, filtersize=9)       # > supported window
+
+
+def test_smooth_element_i420(ctx, orc, rng):
+    w, h, n = 70, 34, 2
+    s0, h2 = 72, 34
+    cw, ch, s1 = 35, 17, 36
+    size = s0 * h2 + 2 * s1 * ch
+    fr = np.stack([_plateaus(rng, 1, size)[0] for _ in range(n)])
+    e = ctx.element("smooth")
+    e.set_caps("I420", "I420", w, h)
+    for luma_only in (True, False):
+        e.set_property("luma-only", 1 if luma_only else 0)
+        d_in, d_out = up(ctx, fr), up(ctx, np.full_like(fr, 77))
+        e.transform_device(d_in, d_out, n)
+        got = ctx.download(d_out, fr.size).reshape(n, size)
+        for f in range(n):
+            y = orc.smooth_plane(fr[f][: s0 * h].reshape(h, s0), w, h, 8, 3, 77)
+            assert np.array_equal(got[f][: s0 * h].reshape(h, s0)[:, :w], y[:, :w]), (luma_only, f)
+            for off in (s0 * h2, s0 * h2 + s1 * ch):
+                plane = fr[f][off: off + s1 * ch].reshape(ch, s1)
+                g = got[f][off: off + s1 * ch].reshape(ch, s1)
+                if luma_only:
+                    assert np.array_equal(g, plane)          # gst_video_frame_copy_plane
+                else:
+                    assert np.array_equal(g[:, :cw], orc.smooth_plane(plane, cw, ch, 8, 3, 77)[:, :cw])
+    e.set_property("active", 0)
+    out = e.transform(fr, n).reshape(n, size)
+    assert np.array_equal(out, fr)                            # inactive: gst_video_frame_copy
+    e.close()
