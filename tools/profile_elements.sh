@@ -13,6 +13,11 @@ for W in $WHATS; do
     remap_packed) K=remap4_packed_kernel; SZ=8k;;
     gaussblur) K=gaussblur_kernel; SZ=4k;;
     direct) K=bayer2rgb_direct; SZ=4k;;
+    rgb2bayer) K=rgb2bayer_kernel; SZ=4k;;
+    sad) K=sad_kernel; SZ=4k;;
+    videodiff) K=videodiff_kernel; SZ=4k;;
+    zebrastripe) K=zebra_planar_kernel; SZ=4k;;
+    smooth) K=smooth_kernel; SZ=4k;;
     *) K=$W; SZ=4k;;
   esac
   timeout 300 $NCU --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -f -o gpurun_out/${TAG}_${W} \

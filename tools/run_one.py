@@ -1,5 +1,5 @@
 """Runs one element kernel a few times (for ncu -k regex:... captures of kernels bench.py --profile does not reach).
-   python tools/run_one.py gaussblur|dilate|exclusion|chromahold|remap|remap_packed|lut4|direct [4k|8k]"""
+   python tools/run_one.py gaussblur|dilate|exclusion|chromahold|remap|remap_packed|lut4|direct|rgb2bayer|sad|videodiff|zebrastripe|smooth [4k|8k]"""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gst-plugins-bad_b200"))
@@ -27,6 +27,17 @@ elif what == "remap_packed":
     idx = b200vf.gt_resolve_map(b200vf.gt_build_map("fisheye", w, h), w, h, 1)
     pk = torch.from_numpy(b200vf.gt_pack_index(idx, w, h)[0]).cuda()
     f = lambda: ctx.remap_packed(a, b, pk, w, h, nframes=n, stream=st)
+elif what in ("sad", "videodiff", "zebrastripe", "smooth"):        # videofiltersbad / smooth on luma planes (1 B per sample)
+    nl = 32 if size == "4k" else 8
+    la = torch.randint(0, 255, (nl, h, w), dtype=torch.uint8, device="cuda"); lb = torch.randint(0, 255, (nl, h, w), dtype=torch.uint8, device="cuda")
+    lo = torch.empty_like(la); sums = torch.zeros(nl, dtype=torch.int32, device="cuda")
+    f = {"sad": lambda: ctx.sad_u8(la, lb, w, w, h, sums, nframes=nl, stream=st),
+         "videodiff": lambda: ctx.videodiff_luma(la, lb, lo, w, w, h, nframes=nl, stream=st),
+         "zebrastripe": lambda: ctx.zebrastripe(lb, 1, w, w, h, threshold=90, nframes=nl, stream=st),
+         "smooth": lambda: ctx.smooth_plane(la, lo, w, w, h, nframes=2, stream=st)}[what]
+elif what == "rgb2bayer":
+    mosaic = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+    f = lambda: ctx.rgb2bayer(a, 4 * w, mosaic, w, w, h, 0, nframes=n, stream=st)
 elif what == "direct":
     src = torch.randint(0, 255, (8, h, w), dtype=torch.uint8, device="cuda"); dst = torch.empty((8, h, 4 * w), dtype=torch.uint8, device="cuda")
     ctx.set_variant("direct"); f = lambda: ctx.bayer2rgb(src, w, dst, 4 * w, w, h, 0, (0, 1, 2), nframes=8, stream=st)
