@@ -414,6 +414,10 @@ def side_measurements(ctx, torch, b200vf, st, side, peak):
         rec("videodiff_luma_%s" % tag, n, px, 3, t)
         t = timeit(lambda: ctx.zebrastripe(src2, 1, w, w, h, threshold=90, nframes=n, stream=st))
         rec("zebrastripe_%s" % tag, n, px, 2, t)
+        mom = torch.zeros(2 * n, dtype=torch.int64, device="cuda")
+        t = timeit(lambda: ctx.luma_moments(src, w, w, h, mom, nframes=n, stream=st))
+        rec("videoanalyse_moments_%s" % tag, n, px, 1, t)                 # read only: 1 B per sample
+        del mom
         # smooth (gst/smooth): adaptive 7x9 box filter, bound by integer issue (63 compares per sample), not by HBM
         ns = min(n, 8)
         t = timeit(lambda: ctx.smooth_plane(src, lum_out, w, w, h, nframes=ns, stream=st), iters=3)

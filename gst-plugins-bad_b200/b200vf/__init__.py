@@ -89,6 +89,8 @@ _SIGS = {
     "b200vf_zebrastripe": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _i, _i, _i, _vp]),
     "b200vf_videodiff_luma": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _vp]),
     "b200vf_sad_u8": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _vp, _vp]),
+    "b200vf_luma_moments": (_i, [_vp, _vp, _i, _sz, _i, _i, _i, _vp, _vp]),
+    "b200vf_videoanalyse_finish": (_i, [C.c_uint64, C.c_uint64, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b200vf_smooth_plane": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _vp]),
     "b200vf_scenechange_reset": (_i, [_vp]),
     "b200vf_scenechange_update": (_i, [_vp, C.c_double, C.POINTER(_i)]),
@@ -298,6 +300,10 @@ class Context:
     def sad_u8(self, a, b, stride, width, height, sums, nframes=1, frame_stride=None, stream=None):
         fs = frame_stride if frame_stride is not None else stride * height
         check(lib.b200vf_sad_u8(self.h, _ptr(a), stride, fs, _ptr(b), stride, fs, width, height, nframes, _ptr(sums), stream))
+
+    def luma_moments(self, luma, stride, width, height, sums, nframes=1, frame_stride=None, stream=None):
+        fs = frame_stride if frame_stride is not None else stride * height
+        check(lib.b200vf_luma_moments(self.h, _ptr(luma), stride, fs, width, height, nframes, _ptr(sums), stream))
 
     def smooth_plane(self, src, dst, stride, width, height, tolerance=8, filtersize=3, nframes=1, frame_stride=None, stream=None):
         fs = frame_stride if frame_stride is not None else stride * height
@@ -574,6 +580,13 @@ class Element:
         flags = (C.c_int * max(n, 1))()
         lib.b200vf_element_last_events(self.h, flags, n)
         return [bool(flags[i]) for i in range(n)]
+
+
+def videoanalyse_finish(total, total_sq, width, height):
+    """(luma-average, luma-variance) of the videoanalyse element from the two moments (host arithmetic)"""
+    a, v = C.c_double(0), C.c_double(0)
+    check(lib.b200vf_videoanalyse_finish(int(total), int(total_sq), width, height, C.byref(a), C.byref(v)))
+    return a.value, v.value
 
 
 class SceneChange:

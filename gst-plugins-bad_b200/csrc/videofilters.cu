@@ -283,6 +283,60 @@ smooth_kernel (const uint8_t *src, int src_stride, size_t src_fs, uint8_t *dst, 
   }
 }
 
+// ---- videoanalyse (gst/videosignal/gstvideoanalyse.c:206-236) --------------------------------------------
+// The reference walks the luma plane twice: sum, then sum of (avg - d)^2 with avg = sum / (w*h) in int. The second
+// sum is an exact integer identity of the first two moments, N*avg^2 - 2*avg*sum + sum(d^2), so one pass that
+// accumulates sum(d) and sum(d^2) suffices (dp4a: four samples per instruction each); 64-bit atomics per CTA.
+template <int WORDS>
+__global__ void __launch_bounds__ (VF_TX * VF_TY)
+luma_sums_kernel (const uint8_t *a, int a_stride, size_t a_fs, int width, int height, unsigned long long *sums)
+{
+  const int w0 = (blockIdx.x * VF_TX + threadIdx.x) * WORDS;
+  const int j0 = (blockIdx.y * VF_TY + threadIdx.y) * VF_ROWS;
+  const int nwords = width >> 2;
+  const uint8_t *fa = a + (size_t) blockIdx.z * a_fs;
+  uint32_t s1 = 0, s2 = 0;                                   // <= 64 samples per thread: 64 * 65025 fits
+  if (w0 < nwords) {
+    uint32_t va[VF_ROWS][WORDS];
+#pragma unroll
+    for (int r = 0; r < VF_ROWS; r++) {
+#pragma unroll
+      for (int k = 0; k < WORDS; k++) va[r][k] = 0;
+      if (j0 + r >= height) continue;
+      const uint32_t *pa = reinterpret_cast<const uint32_t *> (fa + (size_t) (j0 + r) * a_stride) + w0;
+      if (WORDS == 4 && w0 + 4 <= nwords) { const uint4 q = ld_stream_v4 (pa); va[r][0] = q.x; va[r][1] = q.y; va[r][2] = q.z; va[r][3] = q.w; }
+      else
+#pragma unroll
+        for (int k = 0; k < WORDS; k++) if (w0 + k < nwords) va[r][k] = ldg_u32 (pa + k);
+    }
+#pragma unroll
+    for (int r = 0; r < VF_ROWS; r++)
+#pragma unroll
+      for (int k = 0; k < WORDS; k++) { s1 = __dp4a (va[r][k], 0x01010101u, s1); s2 = __dp4a (va[r][k], va[r][k], s2); }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (width & 3)) {
+    const int i = (nwords << 2) + threadIdx.x;
+    for (int r = 0; r < VF_ROWS; r++) {
+      if (j0 + r >= height) break;
+      const uint32_t v = fa[(size_t) (j0 + r) * a_stride + i];
+      s1 += v; s2 += v * v;
+    }
+  }
+  __shared__ unsigned long long part[2][VF_TX * VF_TY / 32];
+  unsigned long long t1 = s1, t2 = s2;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { t1 += __shfl_xor_sync (0xffffffffu, t1, o); t2 += __shfl_xor_sync (0xffffffffu, t2, o); }
+  const int tid = threadIdx.y * VF_TX + threadIdx.x;
+  if ((tid & 31) == 0) { part[0][tid >> 5] = t1; part[1][tid >> 5] = t2; }
+  __syncthreads ();
+  if (tid < 2) {
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < VF_TX * VF_TY / 32; k++) s += part[tid][k];
+    if (s) atomicAdd (sums + 2 * (size_t) blockIdx.z + tid, s);
+  }
+}
+
 bool aligned16 (const void *p, size_t a, size_t b) { return ((uintptr_t) p) % 16 == 0 && a % 16 == 0 && b % 16 == 0; }
 bool aligned4 (const void *p, size_t a, size_t b) { return ((uintptr_t) p) % 4 == 0 && a % 4 == 0 && b % 4 == 0; }
 
@@ -385,6 +439,40 @@ B200VF_API int b200vf_smooth_plane (b200vf_ctx *ctx, const uint8_t *d_src, int s
   smooth_kernel<<<grid, block, 0, s>>> (d_src, src_stride, src_frame_stride, d_dst, dst_stride, dst_frame_stride, width, height, atol, fs,
       filtersize < 0 ? 1 : 0);
   return b200vf_launched (ctx, "smooth");
+}
+
+// videoanalyse: the two moments of each luma plane; d_sums[2f] = sum, d_sums[2f+1] = sum of squares (device).
+B200VF_API int b200vf_luma_moments (b200vf_ctx *ctx, const uint8_t *d_luma, int stride, size_t frame_stride, int width, int height,
+    int nframes, uint64_t *d_sums, void *stream)
+{
+  B200VF_REQUIRE (ctx && d_luma && d_sums && width > 0 && height > 0 && nframes > 0, B200VF_E_INVAL, "luma_moments: bad argument");
+  B200VF_REQUIRE (stride >= width && aligned4 (d_luma, (size_t) stride, frame_stride), B200VF_E_INVAL,
+      "luma_moments: plane and pitch must be 4-byte aligned, pitch >= width");
+  B200VF_REQUIRE (height <= 65535 * VF_TY * VF_ROWS && nframes <= 65535, B200VF_E_UNSUPPORTED, "luma_moments: grid limits");
+  cudaStream_t s = b200vf_stream (ctx, stream);
+  B200VF_CHECK_CUDA (cudaMemsetAsync (d_sums, 0, 2 * sizeof (uint64_t) * (size_t) nframes, s));
+  const dim3 block (VF_TX, VF_TY);
+  unsigned long long *out = reinterpret_cast<unsigned long long *> (d_sums);
+  if (aligned16 (d_luma, (size_t) stride, frame_stride))
+    luma_sums_kernel<4><<<vf_grid (width, height, nframes, 4), block, 0, s>>> (d_luma, stride, frame_stride, width, height, out);
+  else
+    luma_sums_kernel<1><<<vf_grid (width, height, nframes, 1), block, 0, s>>> (d_luma, stride, frame_stride, width, height, out);
+  return b200vf_launched (ctx, "luma_moments");
+}
+
+// gst_video_analyse_planar (:219-220, :232): the element's two numbers from the moments, in the reference's
+// arithmetic: avg = sum / (w*h) in integers; luma_average = sum / (255.0 * w * h); luma_variance =
+// sum ((avg - d)^2) / (255.0 * 255.0 * w * h), the integer sum via N*avg^2 - 2*avg*sum + sum(d^2) (exact).
+B200VF_API int b200vf_videoanalyse_finish (uint64_t sum, uint64_t sum_sq, int width, int height, double *luma_average,
+    double *luma_variance)
+{
+  B200VF_REQUIRE (width > 0 && height > 0 && luma_average && luma_variance, B200VF_E_INVAL, "videoanalyse_finish: bad argument");
+  const uint64_t n = (uint64_t) (width * height);            // the reference's int product
+  const int avg = (int) (sum / n);
+  *luma_average = sum / (255.0 * width * height);
+  const uint64_t var = n * (uint64_t) avg * (uint64_t) avg + sum_sq - 2ull * (uint64_t) avg * sum;
+  *luma_variance = var / (255.0 * 255.0 * width * height);
+  return B200VF_OK;
 }
 
 // gst_scene_change_transform_frame_ip, gstscenechange.c:196-236: the decision on the frame score

@@ -285,6 +285,17 @@ typedef struct b200vf_scenechange_state { double diffs[B200VF_SC_N_DIFFS]; int n
 int b200vf_scenechange_reset (b200vf_scenechange_state *st);
 int b200vf_scenechange_update (b200vf_scenechange_state *st, double score, int *change_out);
 
+/* ------------------------------------------------------- videosignal plugin
+ * videoanalyse: gst_video_analyse_planar (gst/videosignal/gstvideoanalyse.c:
+ * 206-236). b200vf_luma_moments: d_sums[2f] = sum of the luma samples of frame
+ * f, d_sums[2f+1] = sum of their squares (uint64, device memory; one pass).
+ * b200vf_videoanalyse_finish (host): the element's `luma-average` and
+ * `luma-variance` from them, in the reference's arithmetic (integer avg). */
+int b200vf_luma_moments (b200vf_ctx *ctx, const uint8_t *d_luma, int stride, size_t frame_stride, int width, int height,
+    int nframes, uint64_t *d_sums, void *stream);
+int b200vf_videoanalyse_finish (uint64_t sum, uint64_t sum_sq, int width, int height, double *luma_average,
+    double *luma_variance);
+
 /* ------------------------------------------------------------ smooth plugin
  * smooth_filter (gst/smooth/gstsmooth.c:131-176) on one 8-bit plane: the mean
  * (integer division) of the reference sample and of the window samples within

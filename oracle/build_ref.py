@@ -468,6 +468,20 @@ TUS["ref_scenechange.c"] = lambda: (
     + "  }\n  return change;\n}\n")
 
 
+TUS["ref_videoanalyse.c"] = lambda: (
+    "#include <glib.h>\n" + VF_FRAME_SHIM
+    + "typedef struct { double luma_average, luma_variance; } GstVideoAnalyse;\n"
+    + func("gst/videosignal/gstvideoanalyse.c", "gst_video_analyse_planar")
+    + """
+void ref_videoanalyse (guint8 *luma, int stride, int width, int height, double *average, double *variance)
+{
+  GstVideoAnalyse va; GstVideoFrame f;
+  f.info.width = width; f.info.height = height; f.info.stride[0] = stride; f.data[0] = luma;
+  gst_video_analyse_planar (&va, &f);
+  *average = va.luma_average; *variance = va.luma_variance;
+}
+""")
+
 TUS["ref_smooth.c"] = lambda: (
     "#include <glib.h>\n"
     + func("gst/smooth/gstsmooth.c", "smooth_filter")

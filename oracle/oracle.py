@@ -218,6 +218,13 @@ class Port(_Base):
         self.lib.oracle_sad_u8.restype = C.c_uint32
         return int(self.lib.oracle_sad_u8(_p(a), a.shape[1], _p(b), b.shape[1], width, height))
 
+    def videoanalyse(self, luma, width, height):
+        """(luma-average, luma-variance) as the element posts them"""
+        luma = _u8(luma)
+        a, v = C.c_double(0), C.c_double(0)
+        self.lib.oracle_videoanalyse(_p(luma), luma.shape[1], width, height, C.byref(a), C.byref(v))
+        return a.value, v.value
+
     def smooth_plane(self, plane, width, height, tolerance=8, filtersize=3, prefill=0):
         """returns the filtered plane; rows the reference never writes keep `prefill`"""
         plane = _u8(plane)
@@ -403,6 +410,12 @@ class Ref(_Base):
         self.lib.ref_scenechange_score.restype = C.c_double
         self.lib.ref_scenechange_score(_p(a), a.shape[1], _p(b), b.shape[1], width, height, C.byref(sad))
         return int(sad.value)
+
+    def videoanalyse(self, luma, width, height):
+        luma = _u8(luma)
+        a, v = C.c_double(0), C.c_double(0)
+        self.lib.ref_videoanalyse(_p(luma), luma.shape[1], width, height, C.byref(a), C.byref(v))
+        return a.value, v.value
 
     def smooth_plane(self, plane, width, height, tolerance=8, filtersize=3, prefill=0):
         plane = _u8(plane)

@@ -604,3 +604,21 @@ oracle_smooth_plane (uint8_t *dest, const uint8_t *src, int width, int height, i
     }
   }
 }
+
+/* videoanalyse: gst/videosignal/gstvideoanalyse.c:206-236 (two passes, integer average) */
+EXPORT void
+oracle_videoanalyse (const uint8_t *luma, int stride, int width, int height, double *average, double *variance)
+{
+  uint64_t sum = 0;
+  for (int i = 0; i < height; i++)
+    for (int j = 0; j < width; j++) sum += luma[(size_t) i * stride + j];
+  int avg = (int) (sum / (uint64_t) (width * height));
+  *average = sum / (255.0 * width * height);
+  sum = 0;
+  for (int i = 0; i < height; i++)
+    for (int j = 0; j < width; j++) {
+      int diff = avg - luma[(size_t) i * stride + j];
+      sum += (uint64_t) (diff * diff);
+    }
+  *variance = sum / (255.0 * 255.0 * width * height);
+}

@@ -57,6 +57,7 @@ def make_videofilters():
     g["smooth_src"] = sm
     for tol, fs in [(8, 3), (0, 3), (-5, 2), (300, 1), (8, 0), (8, -1), (20, 8)]:
         g["smooth_%d_%d" % (tol, fs)] = R.smooth_plane(sm, w, h, tol, fs, 77)
+    g["va"] = np.array([R.videoanalyse(a, w, h), R.videoanalyse(sm, w, h), R.videoanalyse(np.full((h, st), 255, np.uint8), w, h)], np.float64)
     g["sc_scores"] = scores
     g["sc_changes"] = np.array(R.scenechange_run(scores), np.uint8)
     np.savez_compressed(os.path.join(HERE, "golden_videofilters.npz"), **g)

@@ -255,3 +255,29 @@ def test_smooth_element_i420(ctx, orc, rng):
     out = e.transform(fr, n).reshape(n, size)
     assert np.array_equal(out, fr)                            # inactive: gst_video_frame_copy
     e.close()
+
+
+# ---------------------------------------------------------------- videoanalyse (gst/videosignal)
+@pytest.mark.parametrize("w,h", SIZES)
+def test_videoanalyse_moments(ctx, vf, orc, rng, w, h):
+    st = frames.round_up_4(w)
+    n = 3
+    a = rng.integers(0, 256, (n, h, st), dtype=np.uint8)
+    a[1] = 255
+    d_sums = ctx.alloc(16 * n)
+    ctx.luma_moments(up(ctx, a), st, w, h, d_sums, nframes=n)
+    got = ctx.download(d_sums, 16 * n).view(np.uint64).reshape(n, 2)
+    for f in range(n):
+        x = a[f][:, :w].astype(np.uint64)
+        assert (int(got[f, 0]), int(got[f, 1])) == (int(x.sum()), int((x * x).sum())), (w, h, f)
+        assert vf.videoanalyse_finish(int(got[f, 0]), int(got[f, 1]), w, h) == orc.videoanalyse(a[f], w, h)
+
+
+def test_videoanalyse_8k_needs_64_bit_sums(ctx, vf):
+    w, h = 7680, 4320
+    a = np.full((h, w), 255, np.uint8)
+    d_sums = ctx.alloc(16)
+    ctx.luma_moments(up(ctx, a), w, w, h, d_sums)
+    got = ctx.download(d_sums, 16).view(np.uint64)
+    assert (int(got[0]), int(got[1])) == (255 * w * h, 255 * 255 * w * h)      # 8.5e9 and 2.2e12
+    assert vf.videoanalyse_finish(int(got[0]), int(got[1]), w, h) == (1.0, 0.0)
