@@ -71,6 +71,7 @@ _SIGS = {
     "b200vf_exclusion": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "b200vf_dilate": (_i, [_vp, _vp, _vp, _i, _i, _sz, _i, _i, _vp, _vp]),
     "b200vf_gauss_kernel": (_i, [C.c_float, _vp, _vp, _i]),
+    "b200vf_gaussblur_halo_rows": (_i, [_i, _i, _i, _i]),
     "b200vf_gaussblur": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _sz, _i, _i, _vp, _vp, _i, _i, _vp]),
     "b200vf_gauss_selftest_div": (_i, [_vp, C.c_float, C.c_uint32, C.c_uint32, _vp]),
     "b200vf_gauss_selftest_finish": (_i, [_vp, C.c_uint32, C.c_uint32, _vp]),
@@ -391,6 +392,13 @@ def lut_compose(first, second):
     f, s = _lut_arg(first), _lut_arg(second)
     check(lib.b200vf_lut_compose(_hptr(f), _hptr(s), _hptr(a)))
     return a
+
+
+def gaussblur_halo_rows(windowsize, p0, stride, width):
+    n = lib.b200vf_gaussblur_halo_rows(windowsize, p0, stride, width)
+    if n < 0:
+        check(n)
+    return n
 
 
 def gauss_kernel(sigma):

@@ -58,3 +58,13 @@ B200VF_API int b200vf_gauss_kernel (float sigma, float *kernel, float *kernel_su
   }
   return ws;
 }
+
+// Halo rows a row shard of b200vf_gaussblur must be given above and below (unless at the frame's edge):
+// `center` rows of the window, plus one when the blurred channels start p0 > 0 bytes into the pixel and rows are
+// unpadded - the last p0 bytes of a row's last pixel are then the first bytes of the next row, so the
+// window's outermost rows reach one row further. b200vf_comm_halo_exchange moves exactly these rows.
+B200VF_API int b200vf_gaussblur_halo_rows (int windowsize, int p0, int stride, int width) {
+  B200VF_REQUIRE (windowsize >= 1 && (windowsize & 1) && p0 >= 0 && p0 <= 3 && width > 0 && stride >= 4 * width, B200VF_E_INVAL,
+      "gaussblur_halo_rows: bad argument");
+  return windowsize / 2 + ((p0 > 0 && stride == 4 * width && windowsize > 1) ? 1 : 0);
+}

@@ -176,6 +176,9 @@ int b200vf_dilate (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, int wi
  * first bytes of the next row) must be present around d_src unless at the
  * global edge. */
 int b200vf_gauss_kernel (float sigma, float *kernel, float *kernel_sum, int capacity);
+/* halo rows (above and below) a row shard must be given: windowsize/2, +1 when
+ * p0 > 0 and stride == 4*width (see above); <0 = status */
+int b200vf_gaussblur_halo_rows (int windowsize, int p0, int stride, int width);
 int b200vf_gaussblur (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, int width, int full_height,
     int row0, int rows, int stride, size_t frame_stride, int nframes, int p0,
     const float *kernel, const float *kernel_sum, int windowsize, int exact, void *stream);

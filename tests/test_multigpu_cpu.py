@@ -60,6 +60,13 @@ def _worker(rank, world, port, q):
     fr = rng.integers(0, 256, (h, 4 * w), dtype=np.uint8)
     local, skip = exchange(fr[r0:r0 + rows], 5)
     res["gauss"] = orc.gaussblur(local, w, local.shape[0], 2.0, 0)[skip:skip + rows]
+    # AYUV layout (p0 = 1), unpadded rows: the last channel of a row's last pixel lives in the next row, so the
+    # shard needs one halo row more (b200vf_gaussblur_halo_rows); with only `center` rows the last shard row differs
+    k, _ = b200vf.gauss_kernel(2.0)
+    halo = b200vf.gaussblur_halo_rows(len(k), 1, 4 * w, w)
+    assert halo == 6 and b200vf.gaussblur_halo_rows(len(k), 0, 4 * w, w) == 5 and b200vf.gaussblur_halo_rows(len(k), 1, 4 * w + 16, w) == 5
+    local, skip = exchange(fr[r0:r0 + rows], halo)
+    res["gauss_p1"] = orc.gaussblur(local, w, local.shape[0], 2.0, 1)[skip:skip + rows]
     q.put((rank, r0, rows, res))
     dist.barrier()
     dist.destroy_process_group()
@@ -88,3 +95,4 @@ def test_row_shards_reassemble_to_whole_frame(world):
         assert np.array_equal(cat("bayer_" + fmt), orc.bayer2rgb(mosaic, w, h, fmt, "RGBA")), fmt
     assert np.array_equal(cat("dilate"), orc.dilate(px, False))
     assert np.array_equal(cat("gauss"), orc.gaussblur(fr, w, h, 2.0, 0))
+    assert np.array_equal(cat("gauss_p1"), orc.gaussblur(fr, w, h, 2.0, 1))
