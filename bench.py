@@ -35,8 +35,9 @@ METRIC = "bayer2rgb frames/s (3840x2160 bggr->RGBA)"
 FALLBACK_HBM_GBS = 6650.0
 _json_out = sys.stdout
 # dram__bytes_read.sum + dram__bytes_write.sum of bayer2rgb_tma per 4K frame, from the committed ncu capture
-# profiles/r01_bayer2rgb_tma_final.md (938.2 MB for a 24-frame launch; algorithmic 41.47 MB/frame)
-NCU_TRAFFIC_BYTES_PER_FRAME = 938.21056e6 / 24
+# profiles/r01_bayer2rgb_tma_session2.md (199.10 MB read + 738.68 MB written for a 24-frame launch; algorithmic
+# 41.47 MB/frame: no re-reads, the tail of the writes is still in L2 when the kernel ends)
+NCU_TRAFFIC_BYTES_PER_FRAME = (199.100160e6 + 738.684416e6) / 24
 
 
 def hbm_peak():
