@@ -1,3 +1,9 @@
+"""Splits the SASS page of an ncu capture of gaussblur_kernel into the kernel's phases (developer tool).
+  ncu -i gpurun_out/<tag>_gaussblur.ncu-rep --page source --csv --print-source sass > sass.csv
+  python tools/ncu_regions.py sass.csv <total SMSP cycles of the launch, smsp__cycles_active.sum>
+Per phase: share of the warp-state samples (= warp time), of the executed warp instructions, FMA-pipe cycles
+(FMUL2 / FFMA2 count two) as a fraction of the given cycle count, top stall reasons. The phases are found from
+the positions of the FMUL2 instructions (two dense runs: the horizontal and the vertical tap loop)."""
 import csv,sys
 rows=list(csv.reader(open(sys.argv[1])))
 hdr=rows[1]; data=rows[2:]
