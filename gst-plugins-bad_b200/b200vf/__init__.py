@@ -75,6 +75,8 @@ _SIGS = {
     "b200vf_gaussblur": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _sz, _i, _i, _vp, _vp, _i, _i, _vp]),
     "b200vf_gauss_selftest_div": (_i, [_vp, C.c_float, C.c_uint32, C.c_uint32, _vp]),
     "b200vf_gauss_selftest_finish": (_i, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "b200vf_gauss_selftest_div1": (_i, [_vp, C.c_float, C.c_float, C.c_uint32, C.c_uint32, _vp]),
+    "b200vf_gauss_div1_constant": (_i, [C.c_float, _vp]),
     "b200vf_coloreffects_table": (_i, [_i, C.POINTER(_vp), C.POINTER(_i)]),
     "b200vf_coloreffects_rgb": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "b200vf_coloreffects_ayuv": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _i, _i, _vp, _i, _vp]),
@@ -311,6 +313,12 @@ class Context:
         check(lib.b200vf_smooth_plane(self.h, _ptr(src), stride, fs, _ptr(dst), stride, fs, width, height, nframes,
                                       tolerance, filtersize, stream))
 
+    def gauss_selftest_div1(self, divisor, e, lo_bits, hi_bits):
+        """mismatches between RN(a + a*e) and IEEE a / divisor over fp32 bit patterns (the streaming blur's division)"""
+        bad = C.c_ulonglong(0)
+        check(lib.b200vf_gauss_selftest_div1(self.h, float(divisor), float(e), int(lo_bits), int(hi_bits), C.byref(bad)))
+        return int(bad.value)
+
     def gauss_selftest_finish(self, lo_bits=0, hi_bits=0xffffffff):
         """mismatches between the blur's fp32-only final rounding and (guint8) CLAMP (q + 0.5 [fp64], 0, 255)"""
         bad = C.c_ulonglong(0)
@@ -399,6 +407,13 @@ def gaussblur_halo_rows(windowsize, p0, stride, width):
     if n < 0:
         check(n)
     return n
+
+
+def gauss_div1_constant(divisor):
+    """e with a / divisor == RN(a + a*e) over the blur's dividend range, or None when the divisor is not whitelisted"""
+    e = C.c_float(0)
+    rc = lib.b200vf_gauss_div1_constant(C.c_float(divisor), C.byref(e))
+    return np.float32(e.value) if rc == 0 else None
 
 
 def gauss_kernel(sigma):

@@ -188,6 +188,14 @@ int b200vf_gaussblur (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, int
  * (must be 0 over the range the host enables it for, see gaussblur.cu div_rn). */
 int b200vf_gauss_selftest_div (b200vf_ctx *ctx, float divisor, uint32_t lo_bits, uint32_t hi_bits,
     unsigned long long *mismatches);
+/* Test hooks of the streaming blur's interior division: the full kernel sum b that make_gaussian_kernel produces is
+ * within a few ulp of 1.0, and for a whitelist of such b the quotient a / b equals RN (a + a * e) - one FMA - for
+ * a == 0 and every fp32 a in [2^-64, 2^13]. b200vf_gauss_div1_constant returns the whitelisted e for b
+ * (B200VF_E_UNSUPPORTED: not whitelisted, the blur then takes the general kernel); b200vf_gauss_selftest_div1
+ * counts the bit patterns a in [lo_bits, hi_bits) for which RN (a + a * e) differs from IEEE a / divisor. */
+int b200vf_gauss_div1_constant (float divisor, float *e_out);
+int b200vf_gauss_selftest_div1 (b200vf_ctx *ctx, float divisor, float e, uint32_t lo_bits, uint32_t hi_bits,
+    unsigned long long *mismatches);
 /* Test hook: the blur's last step, (guint8) CLAMP (q + 0.5 [double], 0, 255)
  * (gstgaussblur.c:348-351), is computed without fp64; this counts the fp32 bit
  * patterns q in [lo_bits, hi_bits] (inclusive) for which it differs from the

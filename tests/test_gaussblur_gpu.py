@@ -217,3 +217,46 @@ def test_reciprocal_division_is_ieee_exact(ctx, vf):
     assert ndiv > 100
     # the self-test does detect a differing quotient: 2^60 / 2^-100 overflows, where the reciprocal route gives NaN
     assert ctx.gauss_selftest_div(np.float32(2.0 ** -100), 187 << 23, (187 << 23) + 16) == 16
+
+
+def test_one_fma_division_whitelist(ctx, vf):
+    """gaussblur_stream.cuh divides interior outputs by the full kernel sum b with ONE fma: a / b == RN(a + a*e).
+    Every whitelisted (b, e) pair is checked against IEEE division over EVERY dividend the blur can produce
+    (a == 0 and 2^-64 <= a < 2^13, as in test_reciprocal_division_is_ieee_exact); the sums of the usual sigmas
+    must be on the list (else the blur silently takes the slower general kernel)."""
+    lo, hi = (127 - 64) << 23, (127 + 13) << 23
+    listed = 0
+    for bits in range(0x3f800000 - 8, 0x3f800000 + 9):
+        b = np.array([bits], np.uint32).view(np.float32)[0]
+        e = vf.gauss_div1_constant(b)
+        if e is None:
+            continue
+        listed += 1
+        assert ctx.gauss_selftest_div1(b, e, 0, 1) == 0, hex(bits)
+        assert ctx.gauss_selftest_div1(b, e, lo, hi) == 0, (hex(bits), float(e))
+    assert listed >= 5
+    for sigma in [0.3, 0.5, 1.0, 1.2, 2.0, 3.3, 5.0]:
+        k, ks = vf.gauss_kernel(sigma)
+        assert vf.gauss_div1_constant(ks[-1]) is not None, (sigma, float(ks[-1]))
+    # the self-test does see a wrong constant: e = 2^-24 fails for b = 1 - 2^-24 on power-of-two dividends (a tie)
+    b = np.array([0x3f7fffff], np.uint32).view(np.float32)[0]
+    assert ctx.gauss_selftest_div1(b, np.float32(2.0 ** -24), lo, hi) > 0
+
+
+@pytest.mark.parametrize("sigma,p0,w,h", [(5, 1, 300, 200), (1.2, 1, 300, 200), (2.0, 2, 260, 97), (3.3, 0, 132, 70), (5, 3, 128, 64)])
+def test_stream_kernel_is_taken_and_padded_windows_agree(ctx, vf, orc, rng, monkeypatch, sigma, p0, w, h):
+    """exact blur with symmetric non-negative taps and 16-byte aligned rows runs the streaming kernel; a window padded
+    with zero taps to the next instantiated size (and to a larger one) gives the same bytes as the oracle"""
+    fr = frames.random_u8(rng, h, 4 * w)
+    want = orc.gaussblur(fr, w, h, sigma, p0)
+    got = run(ctx, vf, fr, w, h, sigma, p0)
+    assert ctx.last_kernel() in ("gaussblur_exact_stream", "gaussblur_tail_stream", "gaussblur_gap_copy")
+    assert np.array_equal(got, want), np.argwhere(got != want)[:6]
+    monkeypatch.setenv("B200VF_GAUSS_STREAM_C", "13")
+    got = run(ctx, vf, fr, w, h, sigma, p0)
+    assert np.array_equal(got, want), ("padded to 13", np.argwhere(got != want)[:6])
+    monkeypatch.delenv("B200VF_GAUSS_STREAM_C")
+    monkeypatch.setenv("B200VF_GAUSS_NO_STREAM", "1")
+    got = run(ctx, vf, fr, w, h, sigma, p0)
+    assert ctx.last_kernel() in ("gaussblur_exact", "gaussblur_tail", "gaussblur_gap_copy")
+    assert np.array_equal(got, want), ("general kernel", np.argwhere(got != want)[:6])
