@@ -249,8 +249,9 @@ def test_stream_kernel_is_taken_and_padded_windows_agree(ctx, vf, orc, rng, monk
     with zero taps to the next instantiated size (and to a larger one) gives the same bytes as the oracle"""
     fr = frames.random_u8(rng, h, 4 * w)
     want = orc.gaussblur(fr, w, h, sigma, p0)
+    monkeypatch.setenv("B200VF_GAUSS_STREAM_C", "4")     # (also lifts the size threshold below which the general kernel is kept)
     got = run(ctx, vf, fr, w, h, sigma, p0)
-    assert ctx.last_kernel() in ("gaussblur_exact_stream", "gaussblur_tail_stream", "gaussblur_gap_copy")
+    assert ctx.last_kernel() in ("gaussblur_exact_stream", "gaussblur_lastcol_v", "gaussblur_gap_copy")
     assert np.array_equal(got, want), np.argwhere(got != want)[:6]
     monkeypatch.setenv("B200VF_GAUSS_STREAM_C", "13")
     got = run(ctx, vf, fr, w, h, sigma, p0)
@@ -260,3 +261,40 @@ def test_stream_kernel_is_taken_and_padded_windows_agree(ctx, vf, orc, rng, monk
     got = run(ctx, vf, fr, w, h, sigma, p0)
     assert ctx.last_kernel() in ("gaussblur_exact", "gaussblur_tail", "gaussblur_gap_copy")
     assert np.array_equal(got, want), ("general kernel", np.argwhere(got != want)[:6])
+
+
+@pytest.mark.parametrize("p0", [0, 1, 2, 3])
+@pytest.mark.parametrize("w,h,pad", [(256, 100, 0), (257, 70, 12), (384, 64, 0), (131, 40, 4), (640, 33, 0)])
+def test_stream_kernel_edges_and_shards(ctx, vf, orc, rng, monkeypatch, p0, w, h, pad):
+    """the streaming kernel on small frames (size threshold lifted): widths that are multiples of the 128-column strip
+    (aligned column w would be a strip of its own: the edge pixel columns come from gauss_lastcol_*), ragged widths,
+    padded rows, few CTAs (ranges spanning strips and frames), and row shards against the whole-frame oracle"""
+    if (4 * w + pad) % 16:
+        pytest.skip("rows not 16-byte aligned: pre-pass route, general kernel")
+    monkeypatch.setenv("B200VF_GAUSS_STREAM_C", "13")
+    n = 2
+    fr = frames.random_u8(rng, n * h, 4 * w + pad)
+    stride = 4 * w + pad
+    for sigma in (5, 1.2):
+        k, ks = vf.gauss_kernel(sigma)
+        d_src = ctx.upload(fr)
+        d_dst = ctx.alloc(fr.size + 64)
+        for ctas in (None, 3):
+            if ctas:
+                monkeypatch.setenv("B200VF_GAUSS_CTAS", str(ctas))
+            ctx.gaussblur(d_src, d_dst, w, h, stride, p0, k, ks, nframes=n)
+            got = ctx.download(d_dst, fr.size).reshape(n, h, stride)
+            for i in range(n):
+                want = orc.gaussblur(fr[i * h:(i + 1) * h], w, h, sigma, p0)
+                assert np.array_equal(got[i][:, :4 * w + min(pad, p0)], want[:, :4 * w + min(pad, p0)]), (sigma, ctas, i, np.argwhere(got[i] != want)[:6])
+        monkeypatch.delenv("B200VF_GAUSS_CTAS")
+        # two row shards of frame 0 (center+1 halo rows are there: the shard reads them from the frame itself)
+        one = fr[:h]
+        want = orc.gaussblur(one, w, h, sigma, p0)
+        d_one = ctx.upload(one)
+        d_out = ctx.alloc(one.size + 64)
+        cut = (h // 2) & ~1
+        for (row0, rows) in [(0, cut), (cut, h - cut)]:
+            ctx.gaussblur(d_one.ptr + row0 * stride, d_out.ptr + row0 * stride, w, rows, stride, p0, k, ks, row0=row0, rows=rows, full_height=h)
+        got = ctx.download(d_out, one.size).reshape(h, stride)
+        assert np.array_equal(got[:, :4 * w + min(pad, p0)], want[:, :4 * w + min(pad, p0)]), ("shards", sigma, np.argwhere(got != want)[:6])
