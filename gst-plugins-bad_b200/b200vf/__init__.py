@@ -6,6 +6,7 @@ library.  Import fails loudly when the library has not been built, and
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -52,6 +53,18 @@ _SIGS = {
     "b200vf_pool_buf_pitch": (_sz, [_vp]),
     "b200vf_pool_upload": (_i, [_vp, _i, _vp, _sz, _vp]),
     "b200vf_pool_download": (_i, [_vp, _i, _vp, _sz, _vp]),
+    "b200vf_memory_new": (_i, [_vp, _sz, C.POINTER(_vp)]),
+    "b200vf_pool_acquire_memory": (_i, [_vp, C.POINTER(_vp)]),
+    "b200vf_memory_ref": (_vp, [_vp]),
+    "b200vf_memory_unref": (None, [_vp]),
+    "b200vf_memory_size": (_sz, [_vp]),
+    "b200vf_memory_flags": (C.c_uint, [_vp]),
+    "b200vf_memory_is_writable": (_i, [_vp]),
+    "b200vf_memory_pending_stages": (_i, [_vp]),
+    "b200vf_memory_map": (_i, [_vp, _i, C.POINTER(_vp), _vp]),
+    "b200vf_memory_unmap": (_i, [_vp]),
+    "b200vf_ctx_transfer_counts": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "b200vf_element_transform": (_i, [_vp, _vp, _vp, _i, _vp]),
     "b200vf_malloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
     "b200vf_free": (_i, [_vp, _vp]),
     "b200vf_host_alloc": (_i, [_sz, C.POINTER(_vp)]),
@@ -174,9 +187,15 @@ class Context:
         check(lib.b200vf_ctx_create(device, C.byref(h)))
         self.h = h
         self.device = device
+        self._children = weakref.WeakSet()      # elements / buffers / comms: closed before the context
 
     def close(self):
         if self.h:
+            for c in list(self._children):
+                try:
+                    c.close() if hasattr(c, "close") else c.free()
+                except Exception:
+                    pass
             lib.b200vf_ctx_destroy(self.h)
             self.h = None
 
@@ -202,6 +221,18 @@ class Context:
 
     def last_kernel(self):
         return lib.b200vf_ctx_last_kernel(self.h).decode()
+
+    def transfer_counts(self):
+        """(h2d_count, h2d_bytes, d2h_count, d2h_bytes) of the copies made through Memory objects so far"""
+        v = [C.c_uint64(0) for _ in range(4)]
+        check(lib.b200vf_ctx_transfer_counts(self.h, *[C.byref(x) for x in v]))
+        return tuple(int(x.value) for x in v)
+
+    def memory(self, nbytes):
+        return Memory(self, nbytes)
+
+    def pool(self, buf_bytes, n_bufs):
+        return Pool(self, buf_bytes, n_bufs)
 
     def set_variant(self, v):
         check(lib.b200vf_ctx_set_variant(self.h, {"auto": 0, "direct": 1, "tma": 2}.get(v, v)))
@@ -352,11 +383,109 @@ class Context:
         return Element(self, factory)
 
 
+MAP_READ, MAP_WRITE, MAP_DEVICE = 1, 2, 4
+NEED_UPLOAD, NEED_DOWNLOAD = 1, 2
+
+
+class Memory:
+    """b200vf_memory: device storage + lazy pinned staging + transfer flags (the GstMemory of the HBM pool)."""
+
+    def __init__(self, ctx, nbytes=None, handle=None):
+        if handle is None:
+            h = _vp()
+            check(lib.b200vf_memory_new(ctx.h, nbytes, C.byref(h)))
+            handle = h
+        self.h, self.ctx = handle, ctx
+        ctx._children.add(self)
+
+    @property
+    def nbytes(self):
+        return int(lib.b200vf_memory_size(self.h))
+
+    @property
+    def flags(self):
+        return int(lib.b200vf_memory_flags(self.h))
+
+    @property
+    def pending_stages(self):
+        return int(lib.b200vf_memory_pending_stages(self.h))
+
+    def map(self, flags, stream=None):
+        p = _vp()
+        check(lib.b200vf_memory_map(self.h, flags, C.byref(p), stream))
+        return p.value
+
+    def unmap(self):
+        check(lib.b200vf_memory_unmap(self.h))
+
+    def write(self, array, stream=None):
+        """host writer: map WRITE, fill the pinned staging buffer, unmap (marks NEED_UPLOAD; no copy happens yet)"""
+        a = np.ascontiguousarray(array).view(np.uint8).reshape(-1)
+        assert a.size <= self.nbytes
+        p = self.map(MAP_WRITE, stream)
+        C.memmove(p, _hptr(a), a.size)
+        self.unmap()
+
+    def read(self, nbytes=None, stream=None):
+        """host reader: map READ (launches a pending chain, downloads if the device copy is newer), copy out, unmap"""
+        n = self.nbytes if nbytes is None else nbytes
+        p = self.map(MAP_READ, stream)
+        out = np.empty(n, np.uint8)
+        C.memmove(_hptr(out), p, n)
+        self.unmap()
+        return out
+
+    def close(self):
+        if self.h:
+            lib.b200vf_memory_unref(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.close()
+        except Exception:
+            pass
+
+
+class Pool:
+    """b200vf_pool: one HBM slab of equally sized buffers (the GstBufferPool replacement)."""
+
+    def __init__(self, ctx, buf_bytes, n_bufs):
+        h = _vp()
+        check(lib.b200vf_pool_create(ctx.h, buf_bytes, n_bufs, C.byref(h)))
+        self.h, self.ctx = h, ctx
+        self._mems = weakref.WeakSet()
+        ctx._children.add(self)
+
+    def acquire_memory(self):
+        h = _vp()
+        check(lib.b200vf_pool_acquire_memory(self.h, C.byref(h)))
+        m = Memory(self.ctx, handle=h)
+        self._mems.add(m)
+        return m
+
+    def close(self):
+        if self.h:
+            for m in list(self._mems):
+                m.close()
+            lib.b200vf_pool_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.close()
+        except Exception:
+            pass
+
+
 class DeviceBuffer:
     def __init__(self, ctx, nbytes):
         p = _vp()
         check(lib.b200vf_malloc(ctx.h, nbytes, C.byref(p)))
         self.ctx, self.ptr, self.nbytes = ctx, p.value, nbytes
+        ctx._children.add(self)
 
     def free(self):
         if self.ptr and self.ctx.h:
@@ -480,6 +609,7 @@ class Comm:
         h = _vp()
         check(lib.b200vf_comm_create(ctx.h, idb, rank, nranks, C.byref(h)))
         self.h, self.rank, self.nranks = h, rank, nranks
+        ctx._children.add(self)
 
     def halo_exchange(self, buf, row_bytes, rows, halo, frame_stride, nframes=1, stream=None):
         check(lib.b200vf_comm_halo_exchange(self.h, _ptr(buf), row_bytes, rows, halo, frame_stride, nframes, stream))
@@ -549,6 +679,8 @@ class Element:
         h = _vp()
         check(lib.b200vf_element_factory_make(ctx.h if ctx is not None else None, factory.encode(), C.byref(h)))
         self.h, self.ctx, self.factory = h, ctx, factory
+        if ctx is not None:
+            ctx._children.add(self)
 
     def close(self):
         if self.h:
@@ -591,6 +723,10 @@ class Element:
 
     def transform_host_ptr(self, h_in, h_out, nframes):
         check(lib.b200vf_element_transform_host(self.h, h_in, h_out, nframes))
+
+    def transform_mem(self, m_in, m_out, nframes=1, stream=None):
+        """the transform vfunc on Memory objects: frames stay in HBM, per-pixel elements join pending chains"""
+        check(lib.b200vf_element_transform(self.h, m_in.h, m_out.h, nframes, stream))
 
     def transform_device(self, d_in, d_out, nframes=1, stream=None):
         check(lib.b200vf_element_transform_device(self.h, _ptr(d_in), _ptr(d_out), nframes, stream))

@@ -23,6 +23,9 @@ struct b200vf_ctx {
   unsigned int *tile_counters = nullptr;   // ring of work counters for dynamically scheduled kernels
   std::atomic<unsigned int> tile_counter_next{0};   // ops run on several threads
   cudaMemPool_t scratch_pool = nullptr;    // stream-ordered scratch (gaussblur pre-pass ...): never trimmed at synchronisation points
+  // host <-> device transfers made by b200vf_memory (map / unmap): what a pipeline of elements that keeps its frames
+  // in HBM is judged by
+  std::atomic<uint64_t> h2d_count{0}, h2d_bytes{0}, d2h_count{0}, d2h_bytes{0};
 };
 
 void b200vf_set_error (const char *fmt, ...);

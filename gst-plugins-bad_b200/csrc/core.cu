@@ -177,6 +177,7 @@ B200VF_API int b200vf_memcpy_d2h (b200vf_ctx *ctx, void *h_dst, const void *d_sr
 // ----------------------------------------------------------------------- pool
 struct b200vf_pool {
   b200vf_ctx *ctx = nullptr;
+  int device = -1;                 // cached: destroy must not read a context that was destroyed first
   size_t buf_bytes = 0, pitch = 0;
   int n = 0;
   uint8_t *d_base = nullptr;       // one slab: n buffers at a fixed pitch (batch ops index it directly)
@@ -189,6 +190,7 @@ B200VF_API int b200vf_pool_create (b200vf_ctx *ctx, size_t buf_bytes, int n_bufs
   B200VF_REQUIRE (ctx && out && buf_bytes > 0 && n_bufs > 0, B200VF_E_INVAL, "pool_create: bad argument");
   b200vf_pool *p = new b200vf_pool ();
   p->ctx = ctx;
+  p->device = ctx->device;
   p->buf_bytes = buf_bytes;
   p->pitch = (buf_bytes + kSlack + 255) & ~(size_t) 255;   // 256 B aligned: TMA bases, 128-bit vectors
   p->n = n_bufs;
@@ -208,7 +210,7 @@ B200VF_API int b200vf_pool_create (b200vf_ctx *ctx, size_t buf_bytes, int n_bufs
 }
 B200VF_API void b200vf_pool_destroy (b200vf_pool *pool) {
   if (!pool) return;
-  cudaSetDevice (pool->ctx->device);
+  cudaSetDevice (pool->device);
   if (pool->d_base) cudaFree (pool->d_base);
   if (pool->h_base) cudaFreeHost (pool->h_base);
   delete pool;
@@ -249,6 +251,9 @@ B200VF_API void *b200vf_pool_host_ptr (b200vf_pool *pool, int i) {
   }
   return pool->h_base + pool->pitch * i;
 }
+// hooks for b200vf_memory (host/memory.cpp)
+int b200vf_pool_release_index (b200vf_pool *pool, int index) { return b200vf_pool_release (pool, index); }
+b200vf_ctx *b200vf_pool_ctx (b200vf_pool *pool) { return pool ? pool->ctx : nullptr; }
 B200VF_API size_t b200vf_pool_buf_bytes (const b200vf_pool *pool) { return pool ? pool->buf_bytes : 0; }
 B200VF_API size_t b200vf_pool_buf_pitch (const b200vf_pool *pool) { return pool ? pool->pitch : 0; }
 B200VF_API int b200vf_pool_upload (b200vf_pool *pool, int i, const void *host_src, size_t bytes, void *stream) {

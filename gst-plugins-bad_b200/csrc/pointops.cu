@@ -160,16 +160,20 @@ B200VF_API int b200vf_lut_dodge (uint8_t lut[4][256]) {
 B200VF_API int b200vf_lut_chromium (int edge_a, int edge_b, uint8_t lut[4][256]) {
   B200VF_REQUIRE (lut && edge_a >= 0 && edge_a <= 256 && edge_b >= 0 && edge_b <= 256, B200VF_E_PROPERTY,
       "chromium: edge-a %d / edge-b %d not in [0,256]", edge_a, edge_b);
-  static int cos_table[1024];
-  static bool built = false;
-  if (!built) {                                             // setup_cos_table, gstchromium.c:282-291
-    const float pi = 3.141582f;                             // sic, :102
-    for (int angle = 0; angle < 1024; angle++) {
-      float rad = ((float) angle / 512) * pi;
-      cos_table[angle] = (int) (cos (rad) * 512);
+  // setup_cos_table, gstchromium.c:282-291; built once, thread-safely (function-local static initialiser): the LUT
+  // builders are called from any streaming thread
+  struct CosTable {
+    int v[1024];
+    CosTable () {
+      const float pi = 3.141582f;                             // sic, :102
+      for (int angle = 0; angle < 1024; angle++) {
+        float rad = ((float) angle / 512) * pi;
+        v[angle] = (int) (cos (rad) * 512);
+      }
     }
-    built = true;
-  }
+  };
+  static const CosTable table;
+  const int *cos_table = table.v;
   for (int c = 0; c < 256; c++) {
     int v = cos_table[((c + edge_a) + ((c * edge_b) / 2)) & 1023];   // :325-328
     if (v < 0) v = -v;

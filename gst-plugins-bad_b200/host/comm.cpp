@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <string.h>
 #include <mutex>
+#include <string>
 
 namespace {
 
@@ -32,6 +33,7 @@ struct NcclApi {
   ncclResult_t (*AllReduce) (const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString) (ncclResult_t) = nullptr;
   bool ok = false;
+  std::string load_error;          // dlerror() text saved at load time (a second dlerror() call returns NULL)
 };
 
 NcclApi &nccl () {
@@ -40,8 +42,8 @@ NcclApi &nccl () {
   std::call_once (once, [] () {
     const char *names[] = { "libnccl.so.2", "libnccl.so", nullptr };   // soname match reuses a copy torch already loaded
     for (int i = 0; names[i] && !api.handle; i++) api.handle = dlopen (names[i], RTLD_NOW | RTLD_GLOBAL);
-    if (!api.handle) return;
-#define LOAD(field, sym) api.field = (decltype (api.field)) dlsym (api.handle, sym); if (!api.field) return;
+    if (!api.handle) { const char *e = dlerror (); api.load_error = e ? e : "dlopen failed"; return; }
+#define LOAD(field, sym) api.field = (decltype (api.field)) dlsym (api.handle, sym); if (!api.field) { api.load_error = std::string ("missing symbol ") + sym; return; }
     LOAD (GetUniqueId, "ncclGetUniqueId");
     LOAD (CommInitRank, "ncclCommInitRank");
     LOAD (CommDestroy, "ncclCommDestroy");
@@ -66,10 +68,23 @@ NcclApi &nccl () {
     }                                                                                 \
   } while (0)
 
+// inside ncclGroupStart .. ncclGroupEnd: close the group before returning, or later calls on this thread would queue
+// into a group that never ends
+#define NCCL_CHECK_IN_GROUP(expr)                                                     \
+  do {                                                                                \
+    ncclResult_t _r = (expr);                                                         \
+    if (_r != 0) {                                                                    \
+      b200vf_set_error ("%s failed: %s", #expr, nccl ().GetErrorString (_r));         \
+      nccl ().GroupEnd ();                                                            \
+      return B200VF_E_NCCL;                                                           \
+    }                                                                                 \
+  } while (0)
+
 }  // namespace
 
 struct b200vf_comm {
   b200vf_ctx *ctx = nullptr;
+  int device = -1;                 // cached: destroy must not touch a context that was destroyed first
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
   int *d_flag = nullptr;
@@ -79,7 +94,7 @@ struct b200vf_comm {
 
 B200VF_API int b200vf_comm_unique_id (uint8_t id_out[128]) {
   B200VF_REQUIRE (id_out, B200VF_E_INVAL, "comm_unique_id: NULL argument");
-  B200VF_REQUIRE (nccl ().ok, B200VF_E_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror () ? dlerror () : "missing symbols");
+  B200VF_REQUIRE (nccl ().ok, B200VF_E_NCCL, "libnccl.so.2 could not be loaded: %s", nccl ().load_error.c_str ());
   ncclUniqueId id;
   NCCL_CHECK (nccl ().GetUniqueId (&id));
   memcpy (id_out, id.internal, 128);
@@ -88,12 +103,12 @@ B200VF_API int b200vf_comm_unique_id (uint8_t id_out[128]) {
 
 B200VF_API int b200vf_comm_create (b200vf_ctx *ctx, const uint8_t id[128], int rank, int nranks, b200vf_comm **out) {
   B200VF_REQUIRE (ctx && id && out && nranks >= 1 && rank >= 0 && rank < nranks, B200VF_E_INVAL, "comm_create: bad argument");
-  B200VF_REQUIRE (nccl ().ok, B200VF_E_NCCL, "libnccl.so.2 could not be loaded");
+  B200VF_REQUIRE (nccl ().ok, B200VF_E_NCCL, "libnccl.so.2 could not be loaded: %s", nccl ().load_error.c_str ());
   B200VF_CHECK_CUDA (cudaSetDevice (ctx->device));
   ncclUniqueId uid;
   memcpy (uid.internal, id, 128);
   b200vf_comm *c = new b200vf_comm ();
-  c->ctx = ctx; c->rank = rank; c->nranks = nranks;
+  c->ctx = ctx; c->device = ctx->device; c->rank = rank; c->nranks = nranks;
   ncclResult_t r = nccl ().CommInitRank (&c->comm, nranks, uid, rank);
   if (r != 0) {
     b200vf_set_error ("ncclCommInitRank failed: %s", nccl ().GetErrorString (r));
@@ -107,7 +122,7 @@ B200VF_API int b200vf_comm_create (b200vf_ctx *ctx, const uint8_t id[128], int r
 
 B200VF_API void b200vf_comm_destroy (b200vf_comm *comm) {
   if (!comm) return;
-  cudaSetDevice (comm->ctx->device);
+  cudaSetDevice (comm->device);
   if (comm->comm) nccl ().CommDestroy (comm->comm);
   if (comm->d_flag) cudaFree (comm->d_flag);
   if (comm->scratch) cudaFree (comm->scratch);
@@ -154,12 +169,12 @@ B200VF_API int b200vf_comm_halo_exchange (b200vf_comm *comm, uint8_t *d_buf, siz
     B200VF_CHECK_CUDA (cudaMemcpy2DAsync (send_down, hb, last, frame_stride, hb, nframes, cudaMemcpyDeviceToDevice, s));
   NCCL_CHECK (nccl ().GroupStart ());
   if (up >= 0) {
-    NCCL_CHECK (nccl ().Send (send_up, part, ncclUint8, up, comm->comm, s));
-    NCCL_CHECK (nccl ().Recv (recv_up, part, ncclUint8, up, comm->comm, s));
+    NCCL_CHECK_IN_GROUP (nccl ().Send (send_up, part, ncclUint8, up, comm->comm, s));
+    NCCL_CHECK_IN_GROUP (nccl ().Recv (recv_up, part, ncclUint8, up, comm->comm, s));
   }
   if (down < comm->nranks) {
-    NCCL_CHECK (nccl ().Send (send_down, part, ncclUint8, down, comm->comm, s));
-    NCCL_CHECK (nccl ().Recv (recv_down, part, ncclUint8, down, comm->comm, s));
+    NCCL_CHECK_IN_GROUP (nccl ().Send (send_down, part, ncclUint8, down, comm->comm, s));
+    NCCL_CHECK_IN_GROUP (nccl ().Recv (recv_down, part, ncclUint8, down, comm->comm, s));
   }
   NCCL_CHECK (nccl ().GroupEnd ());
   if (up >= 0)
@@ -186,8 +201,8 @@ B200VF_API int b200vf_comm_allgather_rows (b200vf_comm *comm, uint8_t *d_full, s
       int r0 = 0, rn = 0;
       rc = b200vf_shard_rows (full_rows, r, comm->nranks, &r0, &rn);
       if (rc) { nccl ().GroupEnd (); return rc; }
-      NCCL_CHECK (nccl ().Send (base + (size_t) my0 * row_bytes, (size_t) myn * row_bytes, ncclUint8, r, comm->comm, s));
-      NCCL_CHECK (nccl ().Recv (base + (size_t) r0 * row_bytes, (size_t) rn * row_bytes, ncclUint8, r, comm->comm, s));
+      NCCL_CHECK_IN_GROUP (nccl ().Send (base + (size_t) my0 * row_bytes, (size_t) myn * row_bytes, ncclUint8, r, comm->comm, s));
+      NCCL_CHECK_IN_GROUP (nccl ().Recv (base + (size_t) r0 * row_bytes, (size_t) rn * row_bytes, ncclUint8, r, comm->comm, s));
     }
     NCCL_CHECK (nccl ().GroupEnd ());
   }
@@ -214,9 +229,9 @@ B200VF_API int b200vf_comm_exchange_rows (b200vf_comm *comm, uint8_t *d_full, si
       rc = b200vf_shard_rows (full_rows, r, comm->nranks, &r0, &rn);
       if (rc) { nccl ().GroupEnd (); return rc; }
       if (clip (my0, my0 + myn, need_lo[r], need_hi[r], a, b))           // my rows that peer r reads
-        NCCL_CHECK (nccl ().Send (base + (size_t) a * row_bytes, (size_t) (b - a) * row_bytes, ncclUint8, r, comm->comm, s));
+        NCCL_CHECK_IN_GROUP (nccl ().Send (base + (size_t) a * row_bytes, (size_t) (b - a) * row_bytes, ncclUint8, r, comm->comm, s));
       if (clip (r0, r0 + rn, need_lo[comm->rank], need_hi[comm->rank], a, b))   // peer r's rows that I read
-        NCCL_CHECK (nccl ().Recv (base + (size_t) a * row_bytes, (size_t) (b - a) * row_bytes, ncclUint8, r, comm->comm, s));
+        NCCL_CHECK_IN_GROUP (nccl ().Recv (base + (size_t) a * row_bytes, (size_t) (b - a) * row_bytes, ncclUint8, r, comm->comm, s));
     }
     NCCL_CHECK (nccl ().GroupEnd ());
   }

@@ -12,7 +12,9 @@
 // docs/plugins/gst_plugins_cache.json (bayer :2406, coloreffects :3980,
 // gaudieffects :24928, geometrictransform :25379).
 #include "../csrc/common.cuh"
+#include "memory.h"
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <mutex>
@@ -173,6 +175,7 @@ int round_up_4 (int n) { return (n + 3) & ~3; }
 
 struct b200vf_element {
   b200vf_ctx *ctx = nullptr;
+  int device = -1;                         // cached: destroy must not read a context that was destroyed first
   const FactoryDef *def = nullptr;
   std::map<std::string, double> props;
   std::mutex lock;                         // GST_OBJECT_LOCK analogue: setters run on any thread
@@ -239,13 +242,16 @@ int ensure_staging (b200vf_element *e) {
   return B200VF_OK;
 }
 
-int build_index (b200vf_element *e, cudaStream_t s) {
+// P = the property snapshot taken under the element lock together with the need_remap claim (see claim_remap): a
+// setter running on another thread meanwhile sets need_remap again and the next frame rebuilds.
+int build_index (b200vf_element *e, const std::map<std::string, double> &P, cudaStream_t s) {
   // generate_map + per-frame do_map policy, resolved once per (caps, properties)
   const size_t npx = (size_t) e->width * e->height;
   std::vector<const char *> names;
   std::vector<double> values;
-  for (const auto &kv : e->props) {
-    if (kv.first == "off-edge-pixels") continue;
+  int off_edge = 0;
+  for (const auto &kv : P) {
+    if (kv.first == "off-edge-pixels") { off_edge = (int) kv.second; continue; }
     names.push_back (kv.first.c_str ());
     values.push_back (kv.second);
   }
@@ -253,11 +259,12 @@ int build_index (b200vf_element *e, cudaStream_t s) {
   int rc = b200vf_gt_build_map (e->def->name, e->width, e->height, names.data (), values.data (), (int) names.size (), map_xy.data ());
   if (rc) return rc;
   std::vector<int32_t> idx (npx);
-  rc = b200vf_gt_resolve_map (map_xy.data (), e->width, e->height, (int) e->props["off-edge-pixels"], idx.data ());
+  rc = b200vf_gt_resolve_map (map_xy.data (), e->width, e->height, off_edge, idx.data ());
   if (rc) return rc;
   if (e->index_px != npx) {
     if (e->d_index) cudaFree (e->d_index);
     e->d_index = nullptr;
+    e->index_px = 0;
     rc = b200vf_malloc (e->ctx, npx * 4, (void **) &e->d_index);
     if (rc) return rc;
     e->index_px = npx;
@@ -265,8 +272,25 @@ int build_index (b200vf_element *e, cudaStream_t s) {
   // the table is built rarely; a synchronous copy keeps its lifetime trivial
   B200VF_CHECK_CUDA (cudaMemcpyAsync (e->d_index, idx.data (), npx * 4, cudaMemcpyHostToDevice, s));
   B200VF_CHECK_CUDA (cudaStreamSynchronize (s));
-  e->need_remap = false;
   return B200VF_OK;
+}
+
+// needs_remap is claimed and the properties are copied in ONE critical section (the reference holds the object lock
+// across its map rebuild, gstgeometrictransform.c:254-263): a set_property between the two could otherwise be lost,
+// leaving a stale table until the next property change. Returns whether the caller must rebuild.
+bool claim_remap (b200vf_element *e, std::map<std::string, double> &P) {
+  std::lock_guard<std::mutex> g (e->lock);
+  P = e->props;
+  const bool need = e->need_remap || !e->d_index;
+  e->need_remap = false;
+  return need;
+}
+int rebuild_index_if_needed (b200vf_element *e, cudaStream_t s) {
+  std::map<std::string, double> P;
+  if (!claim_remap (e, P)) return B200VF_OK;
+  int rc = build_index (e, P, s);
+  if (rc) { std::lock_guard<std::mutex> g (e->lock); e->need_remap = true; }
+  return rc;
 }
 
 int run (b200vf_element *e, const uint8_t *d_in, uint8_t *d_out, int nframes, cudaStream_t s) {
@@ -421,10 +445,8 @@ int run (b200vf_element *e, const uint8_t *d_in, uint8_t *d_out, int nframes, cu
       return b200vf_smooth_plane (ctx, d_in + off2, s1, e->in_bytes, d_out + off2, s1, e->in_bytes, cw, ch, nframes, tol, fs, s);
     }
     case K_GEOMETRIC: {
-      if (e->need_remap || !e->d_index) {
-        int rc = build_index (e, s);
-        if (rc) return rc;
-      }
+      int rc = rebuild_index_if_needed (e, s);
+      if (rc) return rc;
       uint32_t fill = !strcmp (e->fmt->name, "AYUV") ? 0x808010ffu : 0u;     // GST_WRITE_UINT32_BE (.., 0xff108080), :244-250
       return b200vf_remap (ctx, d_in, d_out, e->d_index, w, h, e->fmt->pstride, e->in_stride, e->in_bytes, nframes, fill, s);
     }
@@ -442,6 +464,7 @@ B200VF_API int b200vf_element_factory_make (b200vf_ctx *ctx, const char *factory
     if (strcmp (f.name, factory)) continue;
     b200vf_element *e = new b200vf_element ();
     e->ctx = ctx;
+    e->device = ctx ? ctx->device : -1;
     e->def = &f;
     for (const auto &p : f.props) e->props[p.name] = p.def;
     *out = e;
@@ -456,7 +479,7 @@ B200VF_API int b200vf_element_factory_make (b200vf_ctx *ctx, const char *factory
 
 B200VF_API void b200vf_element_destroy (b200vf_element *e) {
   if (!e) return;
-  if (e->ctx) cudaSetDevice (e->ctx->device);
+  if (e->device >= 0) cudaSetDevice (e->device);
   free_staging (e);
   for (int i = 0; i < kHostStreams; i++) if (e->hs[i]) cudaStreamDestroy (e->hs[i]);
   if (e->d_index) cudaFree (e->d_index);
@@ -562,7 +585,7 @@ B200VF_API int b200vf_element_set_caps (b200vf_element *e, const char *in_format
     e->in_stride = e->out_stride = round_up_4 (width * e->fmt->pstride);      // default GstVideoInfo stride
     e->in_bytes = e->out_bytes = (size_t) e->in_stride * height;
   }
-  if (width != e->width || height != e->height) e->need_remap = true;
+  if (width != e->width || height != e->height) { std::lock_guard<std::mutex> g (e->lock); e->need_remap = true; }
   e->width = width;
   e->height = height;
   e->negotiated = true;
@@ -581,7 +604,138 @@ B200VF_API int b200vf_element_transform_device (b200vf_element *e, const void *d
   B200VF_REQUIRE (e && d_in && d_out && nframes > 0, B200VF_E_INVAL, "transform: bad argument");
   B200VF_REQUIRE (e->negotiated, B200VF_E_NOT_NEGOTIATED, "%s: not negotiated yet", e->def->name);
   B200VF_REQUIRE (e->ctx, B200VF_E_NO_DEVICE, "%s: element has no device context (there is no CPU path)", e->def->name);
+  {   // transform_frame elements get distinct buffers from the base class; only the transform_frame_ip ones may alias
+    const Kind k = e->def->kind;
+    const bool ip = k == K_COLOREFFECTS || k == K_CHROMAHOLD || k == K_ZEBRASTRIPE || k == K_SCENECHANGE;
+    B200VF_REQUIRE (ip || d_in != d_out, B200VF_E_INVAL, "%s: transform_frame needs distinct input and output buffers", e->def->name);
+  }
   return run (e, (const uint8_t *) d_in, (uint8_t *) d_out, nframes, b200vf_stream (e->ctx, stream));
+}
+
+// ---- transform on memories: frames stay in HBM between elements, per-pixel elements join pending chains ----
+namespace {
+
+bool is_rgb4 (const FormatDef *f) { return f && f->pstride == 4 && strcmp (f->name, "AYUV") != 0; }
+
+// The per-byte-position LUT of a per-channel element at its current properties, if the element is one
+// (burn / dodge / chromium / solarize; coloreffects' per-channel presets on 4-byte RGB: x / alpha untouched).
+// *luma_table is set instead for coloreffects' luma-mapped presets. Returns 0 = not a chainable element / state,
+// 1 = LUT, 2 = luma table, 3 = identity (coloreffects preset none).
+int chainable_stage (b200vf_element *e, const std::map<std::string, double> &P, uint8_t lut[4][256], const uint8_t **luma_table) {
+  auto get = [&] (const char *n) { auto it = P.find (n); return it == P.end () ? 0.0 : it->second; };
+  switch (e->def->kind) {
+    case K_BURN: return b200vf_lut_burn ((int) get ("adjustment"), lut) ? 0 : 1;
+    case K_DODGE: return b200vf_lut_dodge (lut) ? 0 : 1;
+    case K_CHROMIUM: return b200vf_lut_chromium ((int) get ("edge-a"), (int) get ("edge-b"), lut) ? 0 : 1;
+    case K_SOLARIZE: return b200vf_lut_solarize ((int) get ("threshold"), (int) get ("start"), (int) get ("end"), lut) ? 0 : 1;
+    case K_COLOREFFECTS: {
+      if (!is_rgb4 (e->fmt)) return 0;
+      const uint8_t *table = nullptr;
+      int map_luma = 0;
+      if (b200vf_coloreffects_table ((int) get ("preset"), &table, &map_luma)) return 0;
+      if (!table) return 3;
+      if (map_luma) { *luma_table = table; return 2; }
+      for (int v = 0; v < 256; v++) {                          // r = table[3r], g = table[3g+1], b = table[3b+2] (gstcoloreffects.c:351-353)
+        for (int b = 0; b < 4; b++) lut[b][v] = (uint8_t) v;
+        lut[e->fmt->off[0]][v] = table[3 * v]; lut[e->fmt->off[1]][v] = table[3 * v + 1]; lut[e->fmt->off[2]][v] = table[3 * v + 2];
+      }
+      return 1;
+    }
+    default: return 0;
+  }
+}
+
+}  // namespace
+
+B200VF_API int b200vf_element_transform (b200vf_element *e, b200vf_memory *in, b200vf_memory *out, int nframes, void *stream) {
+  B200VF_REQUIRE (e && in && out && nframes > 0, B200VF_E_INVAL, "transform: bad argument");
+  B200VF_REQUIRE (e->negotiated, B200VF_E_NOT_NEGOTIATED, "%s: not negotiated yet", e->def->name);
+  B200VF_REQUIRE (e->ctx, B200VF_E_NO_DEVICE, "%s: element has no device context (there is no CPU path)", e->def->name);
+  B200VF_REQUIRE (in->ctx == e->ctx && out->ctx == e->ctx, B200VF_E_INVAL, "%s: memories of another context", e->def->name);
+  B200VF_REQUIRE (in->bytes >= e->in_bytes * (size_t) nframes && out->bytes >= e->out_bytes * (size_t) nframes, B200VF_E_INVAL,
+      "%s: memories smaller than %d frames of the negotiated caps", e->def->name, nframes);
+  const Kind k = e->def->kind;
+  const bool ip = k == K_COLOREFFECTS || k == K_CHROMAHOLD || k == K_ZEBRASTRIPE || k == K_SCENECHANGE;
+  B200VF_REQUIRE (ip || in != out, B200VF_E_INVAL, "%s: transform_frame needs distinct input and output buffers", e->def->name);
+  cudaStream_t s = b200vf_stream (e->ctx, stream);
+  std::map<std::string, double> P;
+  {
+    std::lock_guard<std::mutex> g (e->lock);
+    P = e->props;
+  }
+  const bool no_defer = getenv ("B200VF_NO_DEFER") != nullptr;     // A/B knob: launch every element as it comes
+
+  // bayer2rgb only records itself: what follows may fold into its kernel (gstbayer2rgb.c:456-487 is the head of
+  // BASELINE.json configs[4])
+  if (k == K_BAYER2RGB && !no_defer) {
+    b200vf_pending *pc = new b200vf_pending ();
+    pc->head = b200vf_pending::BAYER2RGB;
+    pc->src = b200vf_memory_ref (in);
+    pc->width = e->width; pc->height = e->height; pc->nframes = nframes;
+    pc->src_stride = e->in_stride; pc->src_frame_stride = e->in_bytes;
+    pc->dst_stride = e->out_stride; pc->dst_frame_stride = e->out_bytes;
+    pc->pattern = e->bayer_in;
+    pc->off[0] = e->fmt->off[0]; pc->off[1] = e->fmt->off[1]; pc->off[2] = e->fmt->off[2];
+    b200vf_memory_set_pending (out, pc);
+    return B200VF_OK;
+  }
+
+  uint8_t lut[4][256];
+  const uint8_t *luma = nullptr;
+  const int stage = no_defer ? 0 : chainable_stage (e, P, lut, &luma);
+  if (stage) {
+    // join (or start) a chain. `in` holds the chain so far (possibly none); the result is recorded on `out`.
+    b200vf_pending *pc = nullptr;
+    {
+      std::lock_guard<std::mutex> g (in->mu);
+      const b200vf_pending *have = in->pending;
+      const bool joinable = have && (stage != 2 || (have->head == b200vf_pending::BAYER2RGB && !have->has_luma && !have->has_lut &&
+          have->off[0] == e->fmt->off[0] && have->off[1] == e->fmt->off[1] && have->off[2] == e->fmt->off[2])) &&
+          (have->head != b200vf_pending::BAYER2RGB || (have->width == e->width && have->height == e->height && have->nframes == nframes)) &&
+          (have->head != b200vf_pending::LUT_ONLY || have->npix == (size_t) e->width * e->height * nframes);
+      if (joinable) {
+        pc = new b200vf_pending (*have);
+        b200vf_memory_ref (pc->src);
+      }
+    }
+    if (!pc && stage == 1 && e->in_stride == 4 * e->width) {   // a LUT element on materialised bytes starts a chain of its own
+      pc = new b200vf_pending ();
+      pc->head = b200vf_pending::LUT_ONLY;
+      pc->src = b200vf_memory_ref (in);
+      pc->npix = (size_t) e->width * e->height * nframes;
+      pc->stages = 0;
+    }
+    if (pc) {
+      if (stage == 2) { memcpy (pc->luma_table, luma, 768); pc->has_luma = true; }
+      else if (stage == 1) {
+        if (pc->has_lut) { uint8_t merged[4][256]; b200vf_lut_compose (pc->lut, lut, merged); memcpy (pc->lut, merged, sizeof merged); }
+        else { memcpy (pc->lut, lut, sizeof lut); pc->has_lut = true; }
+      }
+      pc->stages++;
+      if (in == out) {
+        // in place: replace the memory's own chain. A LUT_ONLY chain must not read the memory it writes... it may
+        // (lut4 works in place), but its source reference would be the memory itself: materialise instead.
+        if (pc->src == out) { b200vf_memory_unref (pc->src); delete pc; pc = nullptr; }
+        else b200vf_memory_set_pending (out, pc);
+      } else {
+        b200vf_memory_set_pending (out, pc);
+      }
+      if (pc) return B200VF_OK;
+    }
+    if (stage == 3 && in == out) return B200VF_OK;             // preset none, in place: nothing to do
+  }
+
+  // everything else runs now, on the device copies
+  if (in == out) {
+    uint8_t *d = nullptr;
+    int rc = b200vf_memory_device_rw (out, s, &d);
+    return rc ? rc : run (e, d, d, nframes, s);
+  }
+  const uint8_t *d_in = nullptr;
+  uint8_t *d_out = nullptr;
+  int rc = b200vf_memory_device_read (in, s, &d_in);
+  if (!rc) rc = b200vf_memory_device_write (out, s, &d_out);
+  return rc ? rc : run (e, d_in, d_out, nframes, s);
 }
 
 B200VF_API int b200vf_element_transform_host (b200vf_element *e, const void *h_in, void *h_out, int nframes) {
@@ -591,8 +745,8 @@ B200VF_API int b200vf_element_transform_host (b200vf_element *e, const void *h_i
   B200VF_CHECK_CUDA (cudaSetDevice (e->ctx->device));
   int rc = ensure_staging (e);
   if (rc) return rc;
-  if (e->def->kind == K_GEOMETRIC && (e->need_remap || !e->d_index)) {
-    rc = build_index (e, e->hs[0]);
+  if (e->def->kind == K_GEOMETRIC) {
+    rc = rebuild_index_if_needed (e, e->hs[0]);
     if (rc) return rc;
   }
   // frame i rides stream i % 3: H2D, kernel, D2H are stream-ordered per frame and overlap

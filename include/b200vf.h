@@ -49,6 +49,7 @@ typedef struct b200vf_ctx b200vf_ctx;
 typedef struct b200vf_pool b200vf_pool;
 typedef struct b200vf_element b200vf_element;
 typedef struct b200vf_comm b200vf_comm;
+typedef struct b200vf_memory b200vf_memory;
 
 /* ------------------------------------------------------------------ context */
 int b200vf_version (void);                       /* major*100 + minor */
@@ -96,6 +97,42 @@ int b200vf_host_alloc (size_t bytes, void **h_out);               /* pinned */
 int b200vf_host_free (void *h_ptr);
 int b200vf_memcpy_h2d (b200vf_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream);
 int b200vf_memcpy_d2h (b200vf_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream);
+
+/* ------------------------------------------------------- device memory object
+ * What a GstMemory of the HBM pool is (modelled on GstCudaMemory, sys/nvcodec/gstcudamemory.c:
+ * 95-154 alloc, 257-407 map/unmap/transfer flags): device storage is primary, a pinned host staging buffer appears on
+ * the first host map, and two flags say which copy is stale. Elements take memories (b200vf_element_transform), so a
+ * chain of elements keeps its frames in HBM: the only transfers are the upload of what a host writer staged and the
+ * download when a host reader maps.
+ *   map (B200VF_MAP_DEVICE | ...): the HBM address, after uploading staged bytes (NEED_UPLOAD); WRITE marks the
+ *     staging copy stale (NEED_DOWNLOAD)                         - cuda_mem_map with GST_MAP_CUDA, :331-356
+ *   map (READ / WRITE without DEVICE): the pinned staging address, after downloading (NEED_DOWNLOAD) and waiting for
+ *     the stream; unmap of a WRITE map marks the device copy stale (NEED_UPLOAD)     - :357-407
+ * Deferred per-pixel chains: a memory may hold a PENDING chain instead of bytes - bayer2rgb, then at most one
+ * luma-mapped coloreffects preset, then any number of per-channel LUT elements (burn, dodge, chromium, solarize,
+ * coloreffects' per-channel presets); or LUT elements alone. The chain is launched as ONE kernel
+ * (b200vf_bayer2rgb_fused / b200vf_lut4 with the LUTs composed on the host) when the bytes are needed: a map, or an
+ * element that cannot join the chain. `bayer2rgb ! coloreffects ! solarize` (BASELINE.json configs[4]) through
+ * memories is 1 upload, 1 launch, 1 download. The chain holds a reference to its source memory.
+ * Memories are reference counted (GstMiniObject): a pool memory returns to its pool when the last reference goes. */
+#define B200VF_MAP_READ 1
+#define B200VF_MAP_WRITE 2
+#define B200VF_MAP_DEVICE 4
+#define B200VF_MEMORY_NEED_UPLOAD 1
+#define B200VF_MEMORY_NEED_DOWNLOAD 2
+int b200vf_memory_new (b200vf_ctx *ctx, size_t bytes, b200vf_memory **out);     /* zero-filled, + 64 B slack (D5) */
+int b200vf_pool_acquire_memory (b200vf_pool *pool, b200vf_memory **out);        /* B200VF_E_NOMEM when drained */
+b200vf_memory *b200vf_memory_ref (b200vf_memory *mem);
+void b200vf_memory_unref (b200vf_memory *mem);
+size_t b200vf_memory_size (const b200vf_memory *mem);
+unsigned b200vf_memory_flags (const b200vf_memory *mem);
+int b200vf_memory_is_writable (const b200vf_memory *mem);                       /* refcount == 1 (gst_mini_object_is_writable) */
+int b200vf_memory_pending_stages (const b200vf_memory *mem);                    /* elements recorded, not yet launched */
+int b200vf_memory_map (b200vf_memory *mem, int flags, void **data, void *stream);
+int b200vf_memory_unmap (b200vf_memory *mem);
+/* host <-> device copies made through memories on this context so far (tests, bench `e2e`) */
+int b200vf_ctx_transfer_counts (const b200vf_ctx *ctx, uint64_t *h2d_count, uint64_t *h2d_bytes, uint64_t *d2h_count,
+    uint64_t *d2h_bytes);
 
 /* -------------------------------------------------------------- bayer plugin
  * b200vf_bayer2rgb replaces gst_bayer2rgb_process (gst/bayer/gstbayer2rgb.c:
@@ -395,6 +432,10 @@ int b200vf_element_transform_host (b200vf_element *e, const void *h_in, void *h_
 /* The same vfunc on device memory, asynchronous on `stream`. For in-place
  * elements d_out may equal d_in. */
 int b200vf_element_transform_device (b200vf_element *e, const void *d_in, void *d_out, int nframes, void *stream);
+/* The same vfunc on memories (the GstBuffer path of the HBM pool): frames stay in HBM between elements; per-pixel
+ * elements that can join a pending chain only record themselves (see b200vf_memory). in == out for the
+ * transform_frame_ip elements. nframes frames packed back to back in each memory. */
+int b200vf_element_transform (b200vf_element *e, b200vf_memory *in, b200vf_memory *out, int nframes, void *stream);
 /* scenechange only: flags[i] = 1 when frame i of the LAST transform call is a
  * scene change, i.e. where the reference pushes its downstream force-key-unit
  * event (gstscenechange.c:246-257). Returns the number of frames of that call. */
