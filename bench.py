@@ -8,8 +8,11 @@ A step = ONE pass of the hot path over one batch of synthetic frames resident in
 (3840x2160 bggr -> RGBA; the batch is far larger than the 126 MB L2, so no launch is served
 from cache). N = 1: one batched launch of b200vf_bayer2rgb per step (whole frames, TMA kernel).
 N > 1: every frame is row-sharded over the N ranks (one process per GPU); a step is the packed
-NCCL halo exchange of the mosaic's boundary rows + b200vf_bayer2rgb_shard on N x the frames,
-so per-GPU work stays fixed (weak scaling). Timed on the device with CUDA events on the
+NCCL halo exchange of the mosaic's boundary rows (split-phase, on the communicator's own stream:
+the interior rows of every shard are demosaiced while it runs, the two boundary row pairs after
+it) + b200vf_bayer2rgb_shard on N x the frames, so per-GPU work stays fixed (weak scaling).
+After the timed region every rank checks its shard of frame 0 against the oracle
+(`parity_checked`). Timed on the device with CUDA events on the
 launching stream, barrier + synchronize on both sides, max over ranks.
 
 `value` has inputs already in HBM; `e2e` is the same metric through the element mirror's
@@ -34,10 +37,19 @@ W4K, H4K = 3840, 2160
 METRIC = "bayer2rgb frames/s (3840x2160 bggr->RGBA)"
 FALLBACK_HBM_GBS = 6650.0
 _json_out = sys.stdout
-# dram__bytes_read.sum + dram__bytes_write.sum of bayer2rgb_tma per 4K frame, from the committed ncu capture
-# profiles/r01_bayer2rgb_tma_session2.md (199.10 MB read + 738.68 MB written for a 24-frame launch; algorithmic
-# 41.47 MB/frame: no re-reads, the tail of the writes is still in L2 when the kernel ends)
-NCU_TRAFFIC_BYTES_PER_FRAME = (199.100160e6 + 738.684416e6) / 24
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE bayer2rgb_tma launch at this bench's own batch size (384 4K frames),
+# from the committed `ncu --set full` capture profiles/r02_bayer2rgb_tma_384.md; other batch sizes are scaled from it
+# and labelled "extrapolated"
+
+def traffic(frames_per_launch):
+    """(bytes per launch, how it was obtained)"""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_bayer2rgb_tma_384.json")))
+        per = (rec["dram_bytes_read"] + rec["dram_bytes_write"]) / rec["frames"]
+        kind = "ncu capture at this batch size" if rec["frames"] == frames_per_launch else "extrapolated from the %d-frame ncu capture" % rec["frames"]
+        return per * frames_per_launch, kind + " (profiles/r02_bayer2rgb_tma_384.md)"
+    except Exception:
+        return None, "no capture committed"
 
 
 def hbm_peak():
@@ -172,6 +184,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--frames", type=int, default=384, help="4K frames resident per GPU per step")
     ap.add_argument("--no-elements", action="store_true", help="skip the per-element side measurements")
+    ap.add_argument("--halo", default="overlap", choices=["overlap", "serial"],
+                    help="N > 1: split-phase halo exchange overlapped with the interior rows (default) or serialised ahead of the kernel")
     ap.add_argument("--profile", action="store_true",
                     help="only the timed hot-path steps (for runs under ncu: numbers printed there are not bench values)")
     args = ap.parse_args()
@@ -194,6 +208,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    numa = bind_to_gpu_numa_node(local)                                # before any pinned allocation (first touch)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -223,26 +238,36 @@ def main():
         fs = (rows + 2) * w
         src = torch.randint(0, 256, (nfr, rows + 2, w), dtype=torch.uint8, device="cuda", generator=gen)
         dst = torch.empty((nfr, rows, 4 * w), dtype=torch.uint8, device="cuda")
-        idt = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            import ctypes
-            buf = (ctypes.c_uint8 * 128)()
-            b200vf.check(b200vf.lib.b200vf_comm_unique_id(buf))
-            idt = torch.tensor(list(buf), dtype=torch.uint8)
-        idt = idt.cuda()
-        dist.broadcast(idt, 0)
-        import ctypes
-        idb = (ctypes.c_uint8 * 128)(*idt.cpu().tolist())
-        ch = ctypes.c_void_p()
-        b200vf.check(b200vf.lib.b200vf_comm_create(ctx.h, idb, rank, world, ctypes.byref(ch)))
-        comm = ch
 
-        def step():
-            b200vf.check(b200vf.lib.b200vf_comm_halo_exchange(comm, src.data_ptr(), w, rows, 1, fs, nfr, st))
-            ctx.bayer2rgb_shard(src.data_ptr() + w, w, dst, 4 * w, w, h, r0, rows, 0, (0, 1, 2), nframes=nfr,
-                                src_frame_stride=fs, dst_frame_stride=rows * 4 * w, stream=st)
-        parallelism = "%d GPUs, every frame row-sharded (rows %d..%d on rank %d), packed NCCL halo exchange of 1 mosaic row" % (
-            world, r0, r0 + rows, rank)
+        def bcast(id_bytes):
+            t = torch.tensor(list(id_bytes), dtype=torch.uint8).cuda()
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().tolist())
+        comm = b200vf.Comm(ctx, rank, world, bcast)
+        # rows of this shard whose stencil stays inside the shard (the frame's own top / bottom edge needs no neighbour)
+        lo = 0 if rank == 0 else 2
+        hi = rows if rank == world - 1 else rows - 2
+
+        def shard(a, b):                                               # demosaic shard rows [a, b)
+            ctx.bayer2rgb_shard(src.data_ptr() + w * (1 + a), w, dst.data_ptr() + 4 * w * a, 4 * w, w, h, r0 + a, b - a, 0, (0, 1, 2),
+                                nframes=nfr, src_frame_stride=fs, dst_frame_stride=rows * 4 * w, stream=st)
+
+        if args.halo == "serial":
+            def step():
+                comm.halo_exchange(src.data_ptr(), w, rows, 1, fs, nfr, stream=st)
+                shard(0, rows)
+        else:
+            def step():
+                comm.halo_begin(src.data_ptr(), w, rows, 1, fs, nfr, stream=st)     # pack / NCCL / unpack on the comm's stream
+                shard(lo, hi)                                                        # meanwhile: the rows that read no halo
+                comm.halo_end(stream=st)
+                if lo:
+                    shard(0, lo)
+                if hi < rows:
+                    shard(hi, rows)
+        parallelism = "%d GPUs, every frame row-sharded (rows %d..%d on rank %d), packed NCCL halo exchange of 1 mosaic row, %s" % (
+            world, r0, r0 + rows, rank, "serialised ahead of the kernel" if args.halo == "serial" else
+            "split-phase: overlapped with the interior rows, boundary row pairs after it")
 
     def barrier():
         torch.cuda.synchronize()
@@ -285,6 +310,9 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    # ---- parity of what was just timed: this rank's rows of frame 0 against the oracle (checker leg; untimed)
+    parity_ok = check_parity(np, torch, dist, src, dst, w, h, rank, world)
+
     # ---- e2e: the element's transform vfunc on pinned host buffers (H2D + kernel + D2H timed)
     Be = 16
     el = ctx.element("bayer2rgb")
@@ -295,6 +323,7 @@ def main():
     b200vf.check(b200vf.lib.b200vf_host_alloc(Be * w * h * 4, ctypes.byref(hout)))
     np.ctypeslib.as_array(ctypes.cast(hin, ctypes.POINTER(ctypes.c_uint8)), shape=(Be * w * h,))[:] = \
         np.random.default_rng(rank).integers(0, 256, Be * w * h, dtype=np.uint8)
+    np.ctypeslib.as_array(ctypes.cast(hout, ctypes.POINTER(ctypes.c_uint8)), shape=(Be * w * h * 4,))[:] = 0     # first touch on this node
     for _ in range(2):
         el.transform_host_ptr(hin, hout, Be)
     e2e_steps = max(3, min(args.steps, 10))
@@ -308,6 +337,8 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_fps = Be * world * e2e_steps / float(tt.item())
+    # what the host links give this rank while every rank copies at once: the ceiling of the e2e number
+    link = measure_links(torch, dist, b200vf, ctx, hin, hout, Be * w * h, Be * w * h * 4, world, barrier)
     b200vf.lib.b200vf_host_free(hin)
     b200vf.lib.b200vf_host_free(hout)
 
@@ -320,6 +351,11 @@ def main():
     px_per_launch = (nfr // world) * w * h if world > 1 else nfr * w * h
     kernel_ms = ms_per_step                                            # N=1: the step IS the launch (CUDA events around it)
     achieved = px_per_launch * 5 / (kernel_ms * 1e-3) / 1e9
+    traffic_bytes, traffic_kind = traffic(px_per_launch // (w * h))
+    # e2e ceiling from the measured link rates: a frame needs w*h bytes up and 4*w*h bytes down; both engines run at once
+    link_fps = world * min(link["h2d_GBps"] * 1e9 / (w * h), link["d2h_GBps"] * 1e9 / (4 * w * h))
+    limiter = ("host link: D2H (%.1f GB/s per rank with all %d ranks copying) bounds the step at %.0f frames/s; e2e reaches %.0f %% of it"
+               % (link["d2h_GBps"], world, link_fps, 100 * e2e_fps / link_fps))
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -329,13 +365,15 @@ def main():
                    "l2": "inputs+outputs per step = %.1f GB per GPU, far larger than L2 (no flush needed)" % (
                        px_per_launch * 5 / 1e9)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_BYTES_PER_FRAME * (px_per_launch / (w * h)), "traffic_unit": "bytes per launch "
-                     "(ncu dram read+write of the committed capture, scaled by frames per launch)", "peak_kind": peak_kind,
+                     "traffic": traffic_bytes, "traffic_unit": "bytes per launch: ncu dram read+write, " + traffic_kind,
+                     "peak_kind": peak_kind,
                      "note": "5 algorithmic B/px x pixels per launch / CUDA-event launch time; at N>1 the step also "
-                             "contains the halo exchange"},
+                             "contains the (overlapped) halo exchange and the two boundary launches"},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": Be * w * h * world,
-                "d2h_bytes_per_step": Be * w * h * 4 * world,
+                "d2h_bytes_per_step": Be * w * h * 4 * world, "link": link, "numa": numa,
                 "note": "b200vf_element_transform_host: pinned host in/out, 3-stream H2D/kernel/D2H pipeline, %d frames per step per GPU" % Be},
+        "e2e_limiter": limiter,
+        "parity_checked": parity_ok,
         "gpu_launches": launches,
         "clocks": clocks,
     }
@@ -346,13 +384,212 @@ def main():
                                           "ORC C backup, not the ORC JIT" % (n_cpu, dt_cpu)}
         if not args.no_elements:
             try:
+                line["e2e_paths"] = e2e_paths(ctx, np, torch, b200vf)
+            except Exception as ex:
+                line["e2e_paths"] = {"error": str(ex)}
+            try:
                 line["elements"] = side_measurements(ctx, torch, b200vf, st, side, peak)
             except Exception as ex:                                    # side numbers must never sink the headline
                 line["elements"] = {"error": str(ex)}
+            line["summary"] = summary(line)                            # LAST key: survives a tail of the line
     print(json.dumps(line), file=_json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this process (and with it the first touch of its pinned buffers) to the CPUs of the NUMA node the GPU hangs
+    off. Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(hnd).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                                # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return {"node": None, "note": "the platform reports no NUMA node for the GPU (single node or virtualised)"}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+        return {"node": node, "cpus": len(use), "bus": bus}
+    except Exception as ex:
+        return {"node": None, "note": "not bound: %s" % ex}
+
+
+def measure_links(torch, dist, b200vf, ctx, hin, hout, nin, nout, world, barrier):
+    """Pure copies, every rank at once: pinned host -> HBM and HBM -> pinned host, GB/s per rank (min over ranks)."""
+    import ctypes
+    d_in, d_out = ctx.alloc(nin), ctx.alloc(nout)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    out = {}
+
+    def run(up, down, reps=4):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                b200vf.check(b200vf.lib.b200vf_memcpy_h2d(ctx.h, d_in.ptr, hin, nin, s1.cuda_stream))
+            if down:
+                b200vf.check(b200vf.lib.b200vf_memcpy_d2h(ctx.h, hout, d_out.ptr, nout, s2.cuda_stream))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return reps / float(t.item())
+    run(True, True, 1)
+    out["h2d_GBps"] = run(True, False) * nin / 1e9
+    out["d2h_GBps"] = run(False, True) * nout / 1e9
+    both = run(True, True)
+    out["both_h2d_GBps"], out["both_d2h_GBps"] = both * nin / 1e9, both * nout / 1e9
+    out["note"] = "per rank, all ranks copying concurrently (max time over ranks)"
+    d_in.free(); d_out.free()
+    return out
+
+
+def check_parity(np, torch, dist, src, dst, w, h, rank, world):
+    """Bit-exact check of frame 0 as this rank produced it in the timed region against the oracle (test infrastructure,
+    used here as the checker). N > 1: the rank's halo rows hold its neighbours' boundary rows after the exchange, so
+    [halo | shard | halo] is a window of the global frame; the oracle runs on that window (Bayer phase of its first
+    row: odd for every rank but 0) and the rows whose stencil lies inside the window are compared."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    orc = oracle.best()
+    if world == 1:
+        want = orc.bayer2rgb(src[0].cpu().numpy(), w, h, "bggr", "RGBA")
+        ok = bool(np.array_equal(dst[0].cpu().numpy(), want))
+    else:
+        win = src[0].cpu().numpy()                                     # rows r0-1 .. r0+rows of the global frame
+        got = dst[0].cpu().numpy()
+        rows = got.shape[0]
+        if rank == 0:
+            want = orc.bayer2rgb(win[1:], w, rows + 1, "bggr", "RGBA")[:rows]          # global top rule applies as is
+        elif rank == world - 1:
+            want = orc.bayer2rgb(win[:rows + 1], w, rows + 1, "grbg", "RGBA")[1:]      # window starts on an odd row; global bottom rule
+        else:
+            want = orc.bayer2rgb(win, w, rows + 2, "grbg", "RGBA")[1:rows + 1]
+        ok = bool(np.array_equal(got, want))
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(int(t.item()))
+    return ok
+
+
+def e2e_paths(ctx, np, torch, b200vf):
+    """End-to-end numbers of the other host paths a pipeline takes (N = 1, host buffers, transfers timed):
+    the three-element chain of BASELINE.json configs[4] through b200vf_memory objects (frames stay in HBM, the chain is
+    one launch), the same chain without deferral, and bayer2rgb from PAGEABLE host memory (what a sysmem GstBuffer is)."""
+    out = {}
+    w, h = 7680, 4320
+    rng = np.random.default_rng(7)
+    src = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    e1, e2, e3 = ctx.element("bayer2rgb"), ctx.element("coloreffects"), ctx.element("solarize")
+    e1.set_caps("bggr", "BGRx", w, h); e2.set_caps("BGRx", "BGRx", w, h); e3.set_caps("BGRx", "BGRx", w, h)
+    e2.set_property("preset", "sepia")
+    ring = 3
+    m0 = [ctx.memory(w * h) for _ in range(ring)]
+    m1 = [ctx.memory(4 * w * h) for _ in range(ring)]
+    m2 = [ctx.memory(4 * w * h) for _ in range(ring)]
+    sink = np.empty(4 * w * h, np.uint8)
+    import ctypes as C
+
+    for k in range(ring):                                              # the source's frames: written once into the pinned staging
+        p = m0[k].map(b200vf.MAP_WRITE)
+        C.memmove(p, src.ctypes.data, w * h)
+        m0[k].unmap()
+
+    def frame(i, defer):
+        k = i % ring
+        m0[k].map(b200vf.MAP_WRITE)                                    # the source element "writes" the mosaic in place:
+        m0[k].unmap()                                                  # NEED_UPLOAD is set again, the upload happens per frame
+        e1.transform_mem(m0[k], m1[k]); e2.transform_mem(m1[k], m1[k]); e3.transform_mem(m1[k], m2[k])
+        p = m2[k].map(b200vf.MAP_READ)                                 # the sink maps the frame: launch + download + wait
+        sink[0] = C.cast(p, C.POINTER(C.c_uint8))[4 * w * h - 1]       # (reads it in place)
+        m2[k].unmap()
+
+    for name, env in (("chain_8k_memories_fused", None), ("chain_8k_memories_no_defer", "1")):
+        if env:
+            os.environ["B200VF_NO_DEFER"] = env
+        for i in range(2 * ring):                                      # every ring slot allocates its pinned staging on first use
+            frame(i, env is None)
+        c0, l0 = ctx.transfer_counts(), ctx.launch_count()
+        n = 8
+        t0 = time.perf_counter()
+        for i in range(n):
+            frame(i, env is None)
+        dt = time.perf_counter() - t0
+        c1 = ctx.transfer_counts()
+        out[name] = {"fps": n / dt, "launches_per_frame": (ctx.launch_count() - l0) / n, "h2d_per_frame": (c1[0] - c0[0]) / n,
+                     "d2h_per_frame": (c1[2] - c0[2]) / n, "h2d_bytes_per_frame": (c1[1] - c0[1]) / n, "d2h_bytes_per_frame": (c1[3] - c0[3]) / n,
+                     "note": "7680x4320, one frame at a time: upload from and download into the memories' pinned staging"}
+        os.environ.pop("B200VF_NO_DEFER", None)
+    for m in m0 + m1 + m2:
+        m.close()
+    # the chain through three separate element calls on host buffers (round 1's only host path): 3 x (H2D + kernel + D2H)
+    pin = [C.c_void_p() for _ in range(3)]
+    for p_, nb in zip(pin, (w * h, 4 * w * h, 4 * w * h)):
+        b200vf.check(b200vf.lib.b200vf_host_alloc(nb, C.byref(p_)))
+    C.memmove(pin[0], src.ctypes.data, w * h)
+    def hostchain():
+        e1.transform_host_ptr(pin[0], pin[1], 1); e2.transform_host_ptr(pin[1], pin[1], 1); e3.transform_host_ptr(pin[1], pin[2], 1)
+    hostchain()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        hostchain()
+    out["chain_8k_host_buffers_per_element"] = {"fps": 4 / (time.perf_counter() - t0), "note": "every element uploads and downloads its frame"}
+    for p_ in pin:
+        b200vf.lib.b200vf_host_free(p_)
+    # bayer2rgb 4K from pageable memory
+    w, h = W4K, H4K
+    n = 8
+    el = ctx.element("bayer2rgb")
+    el.set_caps("bggr", "RGBA", w, h)
+    a = rng.integers(0, 256, n * w * h, dtype=np.uint8)
+    o = np.zeros(n * w * h * 4, np.uint8)
+    for mode, name in ((0, "bayer2rgb_4k_pageable_unregistered"), (1, "bayer2rgb_4k_pageable_registered_cached")):
+        el.set_host_mode(mode)
+        for _ in range(2):
+            el.transform_host_ptr(a.ctypes.data, o.ctypes.data, n)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            el.transform_host_ptr(a.ctypes.data, o.ctypes.data, n)
+        out[name] = {"fps": 3 * n / (time.perf_counter() - t0)}
+    el.set_host_mode(0)
+    b200vf.lib.b200vf_host_pin_cache_clear()                          # before numpy frees the arrays
+    return out
+
+
+def summary(line):
+    """The numbers of BASELINE.json's configs in one compact object at the END of the line."""
+    el = line.get("elements", {})
+    ep = line.get("e2e_paths", {})
+
+    def g(name, *keys):
+        d = el.get(name) or ep.get(name) or {}
+        return {k: (round(d[k], 4) if isinstance(d.get(k), float) else d.get(k)) for k in keys if k in d}
+    return {
+        "C2_bayer2rgb_4k": {"fps": round(line["value"], 1), "frac_hbm": round(line["roofline"]["frac"], 4), "e2e_fps": round(line["e2e"]["value"], 1)},
+        "C2_bayer2rgb_8k": g("bayer2rgb_8k_tma", "fps", "frac_hbm"),
+        "C3_gaussblur_sigma5_4k_ayuv": g("gaussblur_sigma5_4k_exact", "fps", "frac_fp32", "kernel"),
+        "C3_gaussblur_sigma5_4k_bgrx": g("gaussblur_sigma5_4k_exact_bgrx", "fps", "frac_fp32"),
+        "C3_gaussblur_sigma5_8k_ayuv": g("gaussblur_sigma5_8k_exact", "fps", "frac_fp32"),
+        "C4_fisheye_8k": g("fisheye_8k_remap", "fps", "frac_hbm"),
+        "C4_fisheye_8k_single_frame": g("fisheye_8k_remap_single_frame", "fps", "frac_hbm", "frac_hbm_with_index"),
+        "C5_chain_8k_fused": g("chain_8k_fused", "fps", "frac_hbm"),
+        "C5_chain_8k_unfused": g("chain_8k_unfused", "fps"),
+        "C5_chain_8k_e2e_memories": g("chain_8k_memories_fused", "fps", "launches_per_frame", "h2d_per_frame", "d2h_per_frame"),
+        "C5_chain_8k_e2e_per_element_host": g("chain_8k_host_buffers_per_element", "fps"),
+    }
 
 
 def side_measurements(ctx, torch, b200vf, st, side, peak):
@@ -472,7 +709,20 @@ def side_measurements(ctx, torch, b200vf, st, side, peak):
             t_map = time.perf_counter() - t0
             d_idx = torch.from_numpy(idx).cuda()
             t = timeit(lambda: ctx.remap(a, b, d_idx, w, h, 4, 4 * w, nframes=n4, stream=st))
-            rec("fisheye_8k_remap", n4, px, 8, t, {"host_map_build_s": t_map, "index_table_bytes_per_px": 4})
+            rec("fisheye_8k_remap", n4, px, 8, t, {"host_map_build_s": t_map, "index_table_bytes_per_px": 4,
+                                                   "note": "batch of %d frames per launch: the 4 B/px index is shared through L2" % n4})
+            # one frame per launch over a ring of frames larger than L2: the index table (132.7 MB, larger than L2 itself)
+            # comes from HBM for every frame: 8 B/px credited, 12 B/px moved
+            ring = a.shape[0]
+            cnt = [0]
+
+            def one():
+                i = cnt[0] % ring
+                cnt[0] += 1
+                ctx.remap(a[i], b[i], d_idx, w, h, 4, 4 * w, nframes=1, stream=st)
+            t1 = timeit(one, iters=2 * ring)
+            rec("fisheye_8k_remap_single_frame", 1, px, 8, t1, {"frac_hbm_with_index": px * 12 / t1 / 1e9 / peak,
+                                                                  "note": "one frame per launch, ring of %d frames" % ring})
             # the same table step-coded (b200vf_gt_pack_index, optional API: 1.5 B/px of table instead of 4)
             t0 = time.perf_counter()
             packed, raw_groups = b200vf.gt_pack_index(idx, w, h)

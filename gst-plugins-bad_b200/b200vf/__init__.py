@@ -65,6 +65,8 @@ _SIGS = {
     "b200vf_memory_unmap": (_i, [_vp]),
     "b200vf_ctx_transfer_counts": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "b200vf_element_transform": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "b200vf_element_set_host_mode": (_i, [_vp, _i]),
+    "b200vf_host_pin_cache_clear": (_i, []),
     "b200vf_malloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
     "b200vf_free": (_i, [_vp, _vp]),
     "b200vf_host_alloc": (_i, [_sz, C.POINTER(_vp)]),
@@ -116,6 +118,8 @@ _SIGS = {
     "b200vf_comm_destroy": (None, [_vp]),
     "b200vf_shard_rows": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "b200vf_comm_halo_exchange": (_i, [_vp, _vp, _sz, _i, _i, _sz, _i, _vp]),
+    "b200vf_comm_halo_begin": (_i, [_vp, _vp, _sz, _i, _i, _sz, _i, _vp]),
+    "b200vf_comm_halo_end": (_i, [_vp, _vp]),
     "b200vf_comm_barrier": (_i, [_vp, _vp]),
     "b200vf_comm_allgather_rows": (_i, [_vp, _vp, _sz, _i, _sz, _i, _vp]),
     "b200vf_comm_exchange_rows": (_i, [_vp, _vp, _sz, _i, _vp, _vp, _sz, _i, _vp]),
@@ -614,6 +618,12 @@ class Comm:
     def halo_exchange(self, buf, row_bytes, rows, halo, frame_stride, nframes=1, stream=None):
         check(lib.b200vf_comm_halo_exchange(self.h, _ptr(buf), row_bytes, rows, halo, frame_stride, nframes, stream))
 
+    def halo_begin(self, buf, row_bytes, rows, halo, frame_stride, nframes=1, stream=None):
+        check(lib.b200vf_comm_halo_begin(self.h, _ptr(buf), row_bytes, rows, halo, frame_stride, nframes, stream))
+
+    def halo_end(self, stream=None):
+        check(lib.b200vf_comm_halo_end(self.h, stream))
+
     def allgather_rows(self, full, row_bytes, full_rows, frame_stride=0, nframes=1, stream=None):
         check(lib.b200vf_comm_allgather_rows(self.h, _ptr(full), row_bytes, full_rows, frame_stride, nframes, stream))
 
@@ -720,6 +730,9 @@ class Element:
         out = np.empty(out_b * nframes, np.uint8)
         check(lib.b200vf_element_transform_host(self.h, _hptr(a), _hptr(out), nframes))
         return out
+
+    def set_host_mode(self, mode):
+        check(lib.b200vf_element_set_host_mode(self.h, mode))
 
     def transform_host_ptr(self, h_in, h_out, nframes):
         check(lib.b200vf_element_transform_host(self.h, h_in, h_out, nframes))

@@ -208,6 +208,7 @@ struct b200vf_element {
   uint8_t *d_in[kHostStreams] = { nullptr, nullptr, nullptr };
   uint8_t *d_out[kHostStreams] = { nullptr, nullptr, nullptr };
   size_t staged_in = 0, staged_out = 0;
+  int host_mode = 0;                       // b200vf_element_set_host_mode
 };
 
 namespace {
@@ -738,6 +739,59 @@ B200VF_API int b200vf_element_transform (b200vf_element *e, b200vf_memory *in, b
   return rc ? rc : run (e, d_in, d_out, nframes, s);
 }
 
+// ---- pageable caller memory -------------------------------------------------------------------------------
+// A sysmem GstBuffer is pageable: cudaMemcpyAsync from / to it is staged through the driver's bounce buffer and runs
+// synchronously with the host. Buffers of a GstBufferPool recur, so the ranges seen are page-locked in place
+// (cudaHostRegister, ~1 ms per 10 MB once) and kept in a small LRU cache; a range that fails to register (read-only
+// mapping, exotic allocator) is simply copied the slow way.
+namespace {
+struct PinnedRange { const uint8_t *base; size_t bytes; uint64_t stamp; };
+std::mutex g_pin_mu;
+std::vector<PinnedRange> g_pinned;
+uint64_t g_pin_clock = 0;
+const size_t kMaxPinnedRanges = 64;
+
+void pin_cached (const void *ptr, size_t bytes) {
+  const uint8_t *p = (const uint8_t *) ptr;
+  std::lock_guard<std::mutex> g (g_pin_mu);
+  for (auto &r : g_pinned)
+    if (p >= r.base && p + bytes <= r.base + r.bytes) { r.stamp = ++g_pin_clock; return; }
+  // drop ranges this one overlaps (a pool that re-allocated), then the least recently used one when full
+  for (size_t i = 0; i < g_pinned.size ();) {
+    if (p < g_pinned[i].base + g_pinned[i].bytes && g_pinned[i].base < p + bytes) {
+      cudaHostUnregister ((void *) g_pinned[i].base);
+      cudaGetLastError ();                                   // (the memory may have been freed under us: nothing to report)
+      g_pinned.erase (g_pinned.begin () + i);
+    } else i++;
+  }
+  if (g_pinned.size () >= kMaxPinnedRanges) {
+    size_t lru = 0;
+    for (size_t i = 1; i < g_pinned.size (); i++) if (g_pinned[i].stamp < g_pinned[lru].stamp) lru = i;
+    cudaHostUnregister ((void *) g_pinned[lru].base);
+    cudaGetLastError ();
+    g_pinned.erase (g_pinned.begin () + lru);
+  }
+  if (cudaHostRegister ((void *) p, bytes, cudaHostRegisterDefault) == cudaSuccess) g_pinned.push_back ({ p, bytes, ++g_pin_clock });
+  else cudaGetLastError ();
+}
+}  // namespace
+
+// Forget every range (and unlock it): before the caller frees the buffers it let us page-lock.
+B200VF_API int b200vf_host_pin_cache_clear (void) {
+  std::lock_guard<std::mutex> g (g_pin_mu);
+  for (auto &r : g_pinned) { cudaHostUnregister ((void *) r.base); cudaGetLastError (); }
+  g_pinned.clear ();
+  return B200VF_OK;
+}
+
+// mode 0: the caller's host buffers are pinned already (b200vf_host_alloc, a pinned pool) or it accepts staged copies;
+// mode 1: pageable buffers that recur (GstBufferPool): page-lock each range on first sight, LRU cache of 64 ranges.
+B200VF_API int b200vf_element_set_host_mode (b200vf_element *e, int mode) {
+  B200VF_REQUIRE (e && (mode == 0 || mode == 1), B200VF_E_INVAL, "set_host_mode: mode %d", mode);
+  e->host_mode = mode;
+  return B200VF_OK;
+}
+
 B200VF_API int b200vf_element_transform_host (b200vf_element *e, const void *h_in, void *h_out, int nframes) {
   B200VF_REQUIRE (e && h_in && h_out && nframes > 0, B200VF_E_INVAL, "transform: bad argument");
   B200VF_REQUIRE (e->negotiated, B200VF_E_NOT_NEGOTIATED, "%s: not negotiated yet", e->def->name);
@@ -745,6 +799,10 @@ B200VF_API int b200vf_element_transform_host (b200vf_element *e, const void *h_i
   B200VF_CHECK_CUDA (cudaSetDevice (e->ctx->device));
   int rc = ensure_staging (e);
   if (rc) return rc;
+  if (e->host_mode == 1) {
+    pin_cached (h_in, e->in_bytes * (size_t) nframes);
+    if (h_out != h_in) pin_cached (h_out, e->out_bytes * (size_t) nframes);
+  }
   if (e->def->kind == K_GEOMETRIC) {
     rc = rebuild_index_if_needed (e, e->hs[0]);
     if (rc) return rc;

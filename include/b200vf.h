@@ -388,6 +388,12 @@ int b200vf_shard_rows (int height, int rank, int nranks, int *row0, int *rows);
  * ncclSend/ncclRecv per neighbour on `stream`. */
 int b200vf_comm_halo_exchange (b200vf_comm *comm, uint8_t *d_buf, size_t row_bytes, int rows, int halo,
     size_t frame_stride, int nframes, void *stream);
+/* The same exchange in two phases, on the communicator's own stream: begin orders it after the work queued on `stream`
+ * so far, end makes `stream` wait for it. In between the caller launches what does not read the halo rows (the
+ * interior rows of every shard), so pack / NCCL / unpack overlap the kernel instead of preceding it. */
+int b200vf_comm_halo_begin (b200vf_comm *comm, uint8_t *d_buf, size_t row_bytes, int rows, int halo,
+    size_t frame_stride, int nframes, void *stream);
+int b200vf_comm_halo_end (b200vf_comm *comm, void *stream);
 int b200vf_comm_barrier (b200vf_comm *comm, void *stream);
 /* All-gather of row shards (geometrictransform: the gather may read any source row): every rank
  * holds a full-size frame buffer with its own rows [row0,row0+rows) (b200vf_shard_rows) filled in; afterwards
@@ -429,6 +435,12 @@ int b200vf_element_unit_size (const b200vf_element *e, size_t *in_bytes, size_t 
 /* transform / transform_frame / transform_frame_ip on host memory: nframes
  * frames packed back to back; pipelined H2D / kernel / D2H; synchronous. */
 int b200vf_element_transform_host (b200vf_element *e, const void *h_in, void *h_out, int nframes);
+/* How transform_host treats the caller's host buffers: 0 (default) as they are - pinned buffers copy asynchronously,
+ * pageable ones through the driver's staging; 1 = pageable buffers that recur (what a sysmem GstBufferPool hands out):
+ * each range is page-locked in place on first sight (cudaHostRegister) and remembered in an LRU cache of 64 ranges. */
+int b200vf_element_set_host_mode (b200vf_element *e, int mode);
+/* Unlock and forget every range mode 1 page-locked (call before freeing such buffers). */
+int b200vf_host_pin_cache_clear (void);
 /* The same vfunc on device memory, asynchronous on `stream`. For in-place
  * elements d_out may equal d_in. */
 int b200vf_element_transform_device (b200vf_element *e, const void *d_in, void *d_out, int nframes, void *stream);
