@@ -184,8 +184,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--frames", type=int, default=384, help="4K frames resident per GPU per step")
     ap.add_argument("--no-elements", action="store_true", help="skip the per-element side measurements")
-    ap.add_argument("--halo", default="overlap", choices=["overlap", "serial"],
-                    help="N > 1: split-phase halo exchange overlapped with the interior rows (default) or serialised ahead of the kernel")
+    ap.add_argument("--halo", default="auto", choices=["auto", "overlap", "serial"],
+                    help="N > 1: split-phase halo exchange overlapped with the interior rows, or serialised ahead of the kernel; "
+                         "auto = overlap from 4 GPUs on (measured, profiles/r02_scaling.md: equal at 8, the two extra boundary launches cost 0.9 %% at 2)")
     ap.add_argument("--profile", action="store_true",
                     help="only the timed hot-path steps (for runs under ncu: numbers printed there are not bench values)")
     args = ap.parse_args()
@@ -252,6 +253,8 @@ def main():
             ctx.bayer2rgb_shard(src.data_ptr() + w * (1 + a), w, dst.data_ptr() + 4 * w * a, 4 * w, w, h, r0 + a, b - a, 0, (0, 1, 2),
                                 nframes=nfr, src_frame_stride=fs, dst_frame_stride=rows * 4 * w, stream=st)
 
+        if args.halo == "auto":
+            args.halo = "overlap" if world >= 4 else "serial"
         if args.halo == "serial":
             def step():
                 comm.halo_exchange(src.data_ptr(), w, rows, 1, fs, nfr, stream=st)
