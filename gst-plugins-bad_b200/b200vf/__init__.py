@@ -67,6 +67,8 @@ _SIGS = {
     "b200vf_element_transform": (_i, [_vp, _vp, _vp, _i, _vp]),
     "b200vf_element_set_host_mode": (_i, [_vp, _i]),
     "b200vf_host_pin_cache_clear": (_i, []),
+    "b200vf_element_default_layout": (_i, [_vp, _i, _vp]),
+    "b200vf_element_transform_host_layout": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "b200vf_malloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
     "b200vf_free": (_i, [_vp, _vp]),
     "b200vf_host_alloc": (_i, [_sz, C.POINTER(_vp)]),
@@ -652,6 +654,11 @@ def shard_rows(height, rank, nranks):
     return r0.value, r.value
 
 
+class FrameLayout(C.Structure):
+    _fields_ = [("n_planes", C.c_int), ("offset", C.c_size_t * 4), ("stride", C.c_int * 4), ("row_bytes", C.c_int * 4),
+                ("rows", C.c_int * 4)]
+
+
 class FactoryInfo(C.Structure):
     _fields_ = [(n, C.c_char_p) for n in ("factory", "plugin", "plugin_description", "plugin_license", "type_name",
                                            "parent_type_name", "klass", "long_name", "description", "author")] + \
@@ -730,6 +737,16 @@ class Element:
         out = np.empty(out_b * nframes, np.uint8)
         check(lib.b200vf_element_transform_host(self.h, _hptr(a), _hptr(out), nframes))
         return out
+
+    def default_layout(self, side):
+        lay = FrameLayout()
+        check(lib.b200vf_element_default_layout(self.h, side, C.byref(lay)))
+        return lay
+
+    def transform_layout(self, buf_in, lay_in, buf_out, lay_out):
+        """one frame whose planes lie at lay.offset[i] / lay.stride[i] inside the numpy buffers (GstVideoMeta layouts)"""
+        check(lib.b200vf_element_transform_host_layout(self.h, buf_in.ctypes.data, C.byref(lay_in) if lay_in is not None else None,
+                                                       buf_out.ctypes.data, C.byref(lay_out) if lay_out is not None else None))
 
     def set_host_mode(self, mode):
         check(lib.b200vf_element_set_host_mode(self.h, mode))

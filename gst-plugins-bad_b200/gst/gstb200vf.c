@@ -8,13 +8,18 @@
  * templates - all taken from the introspection table of the library (b200vf_factory_*), which is generated from and
  * tested against the reference's own API dump (docs/plugins/gst_plugins_cache.json). The data vfuncs
  * (GstBaseTransform::transform, gst/bayer/gstbayer2rgb.c:456-487; GstVideoFilter::transform_frame[_ip],
- * e.g. gst/gaudieffects/gstburn.c:214-250) map the buffers and hand them to b200vf_element_transform_host, i.e. the
- * sm_100a kernels; start() fails with a GST_ELEMENT_ERROR when there is no sm_100 device (no CPU path), like
+ * e.g. gst/gaudieffects/gstburn.c:214-250) take one of two paths. Buffers of the HBM pool (GstB200vfMemory, negotiated
+ * through the caps feature memory:B200VFMemory and propose / decide_allocation - none of the reference elements
+ * overrides those, SURVEY 8b: the default sysmem pool is what this replaces) go to b200vf_element_transform: the frame
+ * stays in HBM from element to element and per-pixel elements fuse. System-memory buffers are mapped and handed to
+ * b200vf_element_transform_host (page-locked in place on first sight), with the frame's own plane strides / offsets
+ * when a GstVideoMeta moved them (b200vf_element_transform_host_layout). start() fails with a GST_ELEMENT_ERROR when there is no sm_100 device (no CPU path), like
  * sys/nvcodec registers nothing without a driver (sys/nvcodec/plugin.c:72-103).
  *
- * NOT compiled in this repository's CI image (no GLib/GStreamer there): build-gated on
- * `pkg-config gstreamer-video-1.0` in gst/meson.build. The mapping from element state to C-ABI calls is the one
- * host/elements.cpp exercises on the GPU in tests/test_elements_gpu.py.
+ * There is no GLib / GStreamer in this repository's CI image: the file is compile-checked there against
+ * the declaration-only headers of tests/stubs/ (tests/test_shells_cpu.py: every plugin variant, -Wall -Werror) and built
+ * for real by gst/meson.build where `pkg-config gstreamer-video-1.0` exists. The mapping from element state to C-ABI
+ * calls is the one host/elements.cpp exercises on the GPU in tests/test_elements_gpu.py / test_memory_gpu.py.
  */
 #ifdef HAVE_CONFIG_H
 #include "config.h"
@@ -25,6 +30,7 @@
 #include <gst/video/video.h>
 #include <gst/video/gstvideofilter.h>
 #include "b200vf.h"
+#include "gstb200vfmemory.h"
 
 #ifndef B200VF_PLUGIN
 #error "compile with -DB200VF_PLUGIN=bayer|gaudieffects|coloreffects|geometrictransform|videofiltersbad"
@@ -48,6 +54,7 @@ typedef struct
   b200vf_element *el;
   gint device;
   guint key_unit_count;         /* scenechange: running count of the force-key-unit events (gstscenechange.c:255) */
+  gboolean hbm_out;             /* decide_allocation settled on the HBM pool for the src side */
 } GstB200vf;
 
 typedef struct
@@ -68,11 +75,34 @@ is_bayer_plugin_factory (const gchar * f)
 }
 
 /* ---- properties: straight through to the element mirror (which validates ranges like GParamSpec does) ---- */
+/* perspective's only own property is `matrix`, a GValueArray of 9 doubles (gstperspective.c:97-176, 222-233); the mirror
+ * keeps the nine coefficients as matrix-0 .. matrix-8 */
+static gboolean
+is_matrix_property (GParamSpec * pspec)
+{
+  return !strcmp (pspec->name, "matrix");
+}
+
 static void
 b200vf_set_property (GObject * object, guint id, const GValue * value, GParamSpec * pspec)
 {
   GstB200vf *self = B200VF (object);
   gdouble v = 0;
+  if (is_matrix_property (pspec)) {
+    GValueArray *va = g_value_get_boxed (value);
+    if (!va || va->n_values != 9) {
+      GST_WARNING_OBJECT (self, "matrix: invalid number of elements: %u", va ? va->n_values : 0);     /* set_matrix_from_array, :114-135 */
+      return;
+    }
+    GST_OBJECT_LOCK (self);
+    for (guint i = 0; i < 9; i++) {
+      gchar name[16];
+      g_snprintf (name, sizeof name, "matrix-%u", i);
+      b200vf_element_set_property (self->el, name, g_value_get_double (g_value_array_get_nth (va, i)));
+    }
+    GST_OBJECT_UNLOCK (self);
+    return;
+  }
   if (G_VALUE_HOLDS_UINT (value)) v = g_value_get_uint (value);
   else if (G_VALUE_HOLDS_INT (value)) v = g_value_get_int (value);
   else if (G_VALUE_HOLDS_BOOLEAN (value)) v = g_value_get_boolean (value);
@@ -89,6 +119,21 @@ b200vf_get_property (GObject * object, guint id, GValue * value, GParamSpec * ps
 {
   GstB200vf *self = B200VF (object);
   gdouble v = 0;
+  if (is_matrix_property (pspec)) {         /* get_array_from_matrix, :96-112 */
+    GValueArray *va = g_value_array_new (1);
+    for (guint i = 0; i < 9; i++) {
+      GValue d = G_VALUE_INIT;
+      gchar name[16];
+      g_snprintf (name, sizeof name, "matrix-%u", i);
+      b200vf_element_get_property (self->el, name, &v);
+      g_value_init (&d, G_TYPE_DOUBLE);
+      g_value_set_double (&d, v);
+      g_value_array_append (va, &d);
+      g_value_unset (&d);
+    }
+    g_value_take_boxed (value, va);
+    return;
+  }
   b200vf_element_get_property (self->el, pspec->name, &v);
   if (G_VALUE_HOLDS_UINT (value)) g_value_set_uint (value, (guint) v);
   else if (G_VALUE_HOLDS_INT (value)) g_value_set_int (value, (gint) v);
@@ -203,6 +248,8 @@ b200vf_start (GstBaseTransform * base)
     if (b200vf_element_get_property (old, p.name, &v) == B200VF_OK) b200vf_element_set_property (self->el, p.name, v);
   }
   b200vf_element_destroy (old);
+  /* sysmem GstBuffers are pageable and recur (buffer pools): page-lock each range on first sight */
+  b200vf_element_set_host_mode (self->el, 1);
   return TRUE;
 }
 
@@ -230,30 +277,99 @@ b200vf_flow (GstB200vf * self, int rc)
   return GST_FLOW_ERROR;
 }
 
-static GstFlowReturn
-b200vf_transform_frame (GstVideoFilter * vf, GstVideoFrame * in, GstVideoFrame * out)
+/* the frame's plane strides / offsets against the layout the library assumes; *differs = the frame needs
+ * b200vf_element_transform_host_layout */
+static void
+frame_layout (GstB200vf * self, int side, GstVideoFrame * frame, b200vf_frame_layout * lay, gboolean * differs)
 {
-  return b200vf_flow (B200VF (vf), b200vf_element_transform_host (B200VF (vf)->el,
-          GST_VIDEO_FRAME_PLANE_DATA (in, 0), GST_VIDEO_FRAME_PLANE_DATA (out, 0), 1));
+  b200vf_frame_layout def;
+  guint8 *base = GST_VIDEO_FRAME_PLANE_DATA (frame, 0);
+  memset (lay, 0, sizeof *lay);
+  *differs = FALSE;
+  if (b200vf_element_default_layout (self->el, side, &def) != B200VF_OK) return;
+  lay->n_planes = (int) GST_VIDEO_FRAME_N_PLANES (frame);
+  if (lay->n_planes != def.n_planes) *differs = TRUE;
+  for (gint i = 0; i < lay->n_planes && i < 4; i++) {
+    lay->offset[i] = (size_t) ((guint8 *) GST_VIDEO_FRAME_PLANE_DATA (frame, i) - base);
+    lay->stride[i] = GST_VIDEO_FRAME_PLANE_STRIDE (frame, i);
+    if (i < def.n_planes && (lay->offset[i] != def.offset[i] || lay->stride[i] != def.stride[i])) *differs = TRUE;
+  }
 }
 
-/* (planar YUV frames of the videofiltersbad elements: the planes of a default-layout GstVideoInfo are contiguous
- * from plane 0, which is the layout the element mirror computes; a buffer with a GstVideoMeta that moves planes
- * would be copied into that layout first - not needed for videotestsrc / decoders' default pools) */
-static GstFlowReturn
-b200vf_transform_frame_ip (GstVideoFilter * vf, GstVideoFrame * frame)
+static void
+push_scenechange_event (GstB200vf * self, GstBuffer * buf)
 {
-  GstB200vf *self = B200VF (vf);
-  guint8 *d = GST_VIDEO_FRAME_PLANE_DATA (frame, 0);
-  GstFlowReturn ret = b200vf_flow (self, b200vf_element_transform_host (self->el, d, d, 1));
   /* scenechange: the detection becomes a downstream force-key-unit event (gstscenechange.c:246-257) */
-  if (ret == GST_FLOW_OK && !strcmp (B200VF_GET_CLASS (self)->factory, "scenechange")) {
-    int changed = 0;
-    if (b200vf_element_last_events (self->el, &changed, 1) == 1 && changed)
-      gst_pad_push_event (GST_BASE_TRANSFORM_SRC_PAD (self),
-          gst_video_event_new_downstream_force_key_unit (GST_BUFFER_PTS (frame->buffer), GST_CLOCK_TIME_NONE,
-              GST_CLOCK_TIME_NONE, FALSE, self->key_unit_count++));
+  int changed = 0;
+  if (strcmp (B200VF_GET_CLASS (self)->factory, "scenechange")) return;
+  if (b200vf_element_last_events (self->el, &changed, 1) == 1 && changed)
+    gst_pad_push_event (GST_BASE_TRANSFORM_SRC_PAD (self),
+        gst_video_event_new_downstream_force_key_unit (GST_BUFFER_PTS (buf), GST_CLOCK_TIME_NONE,
+            GST_CLOCK_TIME_NONE, FALSE, self->key_unit_count++));
+}
+
+/* GstVideoFilter elements: GstBaseTransform::transform / transform_ip are overridden (instead of transform_frame[_ip])
+ * because GstVideoFilter maps both buffers to system memory before it calls transform_frame - for buffers of the HBM
+ * pool that would download every frame. */
+static GstFlowReturn
+b200vf_vf_transform (GstBaseTransform * base, GstBuffer * inbuf, GstBuffer * outbuf)
+{
+  GstB200vf *self = B200VF (base);
+  GstVideoFilter *vf = GST_VIDEO_FILTER_CAST (base);
+  b200vf_memory *min = gst_b200vf_buffer_peek (inbuf), *mout = gst_b200vf_buffer_peek (outbuf);
+  GstVideoFrame fin, fout;
+  b200vf_frame_layout lin, lout;
+  gboolean din, dout;
+  int rc;
+  if (!vf->negotiated) return GST_FLOW_NOT_NEGOTIATED;
+  if (min && mout)              /* HBM in, HBM out: nothing crosses PCIe, per-pixel elements only record themselves */
+    return b200vf_flow (self, b200vf_element_transform (self->el, min, mout, 1, NULL));
+  if (!gst_video_frame_map (&fin, &vf->in_info, inbuf, GST_MAP_READ)) goto map_failed;
+  if (!gst_video_frame_map (&fout, &vf->out_info, outbuf, GST_MAP_WRITE)) {
+    gst_video_frame_unmap (&fin);
+    goto map_failed;
   }
+  frame_layout (self, 0, &fin, &lin, &din);
+  frame_layout (self, 1, &fout, &lout, &dout);
+  if (din || dout)
+    rc = b200vf_element_transform_host_layout (self->el, GST_VIDEO_FRAME_PLANE_DATA (&fin, 0), &lin, GST_VIDEO_FRAME_PLANE_DATA (&fout, 0), &lout);
+  else
+    rc = b200vf_element_transform_host (self->el, GST_VIDEO_FRAME_PLANE_DATA (&fin, 0), GST_VIDEO_FRAME_PLANE_DATA (&fout, 0), 1);
+  gst_video_frame_unmap (&fout);
+  gst_video_frame_unmap (&fin);
+  return b200vf_flow (self, rc);
+map_failed:
+  GST_ELEMENT_ERROR (self, CORE, FAILED, (NULL), ("could not map a video frame"));
+  return GST_FLOW_ERROR;
+}
+
+static GstFlowReturn
+b200vf_vf_transform_ip (GstBaseTransform * base, GstBuffer * buf)
+{
+  GstB200vf *self = B200VF (base);
+  GstVideoFilter *vf = GST_VIDEO_FILTER_CAST (base);
+  b200vf_memory *m = gst_b200vf_buffer_peek (buf);
+  GstVideoFrame frame;
+  b200vf_frame_layout lay;
+  gboolean differs;
+  GstFlowReturn ret;
+  int rc;
+  if (!vf->negotiated) return GST_FLOW_NOT_NEGOTIATED;
+  if (m) {
+    ret = b200vf_flow (self, b200vf_element_transform (self->el, m, m, 1, NULL));
+  } else {
+    guint8 *d;
+    if (!gst_video_frame_map (&frame, &vf->in_info, buf, GST_MAP_READWRITE)) {
+      GST_ELEMENT_ERROR (self, CORE, FAILED, (NULL), ("could not map a video frame"));
+      return GST_FLOW_ERROR;
+    }
+    frame_layout (self, 0, &frame, &lay, &differs);
+    d = GST_VIDEO_FRAME_PLANE_DATA (&frame, 0);
+    rc = differs ? b200vf_element_transform_host_layout (self->el, d, &lay, d, &lay) : b200vf_element_transform_host (self->el, d, d, 1);
+    gst_video_frame_unmap (&frame);
+    ret = b200vf_flow (self, rc);
+  }
+  if (ret == GST_FLOW_OK) push_scenechange_event (self, buf);
   return ret;
 }
 
@@ -261,13 +377,27 @@ static GstFlowReturn
 b200vf_bayer_transform (GstBaseTransform * base, GstBuffer * inbuf, GstBuffer * outbuf)
 {
   GstMapInfo in, out;
+  b200vf_memory *min = gst_b200vf_buffer_peek (inbuf), *mout = gst_b200vf_buffer_peek (outbuf);
+  if (min && mout) return b200vf_flow (B200VF (base), b200vf_element_transform (B200VF (base)->el, min, mout, 1, NULL));
   if (!gst_buffer_map (inbuf, &in, GST_MAP_READ)) goto map_failed;
   if (!gst_buffer_map (outbuf, &out, GST_MAP_WRITE)) {
     gst_buffer_unmap (inbuf, &in);
     goto map_failed;
   }
   {
-    int rc = b200vf_element_transform_host (B200VF (base)->el, in.data, out.data, 1);
+    /* the mosaic has no GstVideoInfo: its pitch is GST_ROUND_UP_4 (width) by the element's own contract (:477); the RGB
+     * side takes whatever stride a GstVideoMeta announces */
+    GstVideoMeta *meta = gst_buffer_get_video_meta (outbuf);
+    b200vf_frame_layout lo;
+    int rc;
+    gboolean raw_out = !strcmp (B200VF_GET_CLASS (base)->factory, "bayer2rgb");
+    if (meta && raw_out && b200vf_element_default_layout (B200VF (base)->el, 1, &lo) == B200VF_OK && meta->n_planes == 1 &&
+        (meta->stride[0] != lo.stride[0] || meta->offset[0] != 0)) {
+      lo.stride[0] = meta->stride[0];
+      lo.offset[0] = meta->offset[0];
+      rc = b200vf_element_transform_host_layout (B200VF (base)->el, in.data, NULL, out.data, &lo);
+    } else
+      rc = b200vf_element_transform_host (B200VF (base)->el, in.data, out.data, 1);
     gst_buffer_unmap (outbuf, &out);
     gst_buffer_unmap (inbuf, &in);
     return b200vf_flow (B200VF (base), rc);
@@ -275,6 +405,80 @@ b200vf_bayer_transform (GstBaseTransform * base, GstBuffer * inbuf, GstBuffer * 
 map_failed:
   GST_WARNING_OBJECT (base, "Could not map buffer, skipping");      /* the reference returns OK here (:484-486) */
   return GST_FLOW_OK;
+}
+
+/* ---- allocation: the HBM pool replaces the default system-memory pool (sys/nvcodec/gstcudabasetransform.c:436-587) ---- */
+static gboolean
+caps_have_hbm_feature (GstCaps * caps)
+{
+  GstCapsFeatures *f = (caps && gst_caps_get_size (caps) > 0) ? gst_caps_get_features (caps, 0) : NULL;
+  return f != NULL && gst_caps_features_contains (f, GST_CAPS_FEATURE_MEMORY_B200VF);
+}
+
+static gboolean
+b200vf_propose_allocation (GstBaseTransform * base, GstQuery * decide_query, GstQuery * query)
+{
+  GstB200vf *self = B200VF (base);
+  GstCaps *caps = NULL;
+  gboolean need_pool = FALSE;
+  if (decide_query == NULL) return TRUE;      /* passthrough: upstream and downstream talk to each other */
+  gst_query_parse_allocation (query, &caps, &need_pool);
+  if (caps == NULL) return FALSE;
+  if (caps_have_hbm_feature (caps) && self->ctx && need_pool) {
+    /* upstream produces into HBM: offer it our pool */
+    gsize in_bytes = 0, out_bytes = 0;
+    GstBufferPool *pool = gst_b200vf_buffer_pool_new (self->ctx);
+    GstStructure *config = gst_buffer_pool_get_config (pool);
+    b200vf_element_unit_size (self->el, &in_bytes, &out_bytes);
+    gst_buffer_pool_config_set_params (config, caps, (guint) in_bytes, 0, 0);
+    gst_buffer_pool_config_add_option (config, GST_BUFFER_POOL_OPTION_VIDEO_META);
+    if (!gst_buffer_pool_set_config (pool, config)) {
+      gst_object_unref (pool);
+      return FALSE;
+    }
+    gst_query_add_allocation_pool (query, pool, (guint) in_bytes, 0, 0);
+    gst_object_unref (pool);
+  }
+  /* strides other than the default ones are fine with us (transform_host_layout) */
+  gst_query_add_allocation_meta (query, GST_VIDEO_META_API_TYPE, NULL);
+  return TRUE;
+}
+
+static gboolean
+b200vf_decide_allocation (GstBaseTransform * base, GstQuery * query)
+{
+  GstB200vf *self = B200VF (base);
+  GstCaps *outcaps = NULL;
+  GstBufferPool *pool = NULL;
+  guint size = 0, min = 0, max = 0;
+  gboolean update_pool = FALSE;
+  gst_query_parse_allocation (query, &outcaps, NULL);
+  self->hbm_out = outcaps != NULL && caps_have_hbm_feature (outcaps) && self->ctx != NULL;
+  if (!self->hbm_out)           /* downstream wants system memory: the base class's default video pool */
+    return GST_BASE_TRANSFORM_CLASS (g_type_class_peek_parent (G_OBJECT_GET_CLASS (base)))->decide_allocation (base, query);
+  if (gst_query_get_n_allocation_pools (query) > 0) {
+    gst_query_parse_nth_allocation_pool (query, 0, &pool, &size, &min, &max);
+    update_pool = TRUE;
+    if (pool && !g_type_is_a (G_OBJECT_TYPE (pool), g_type_from_name ("GstB200vfBufferPool"))) {
+      gst_object_unref (pool);  /* somebody else's pool: ours allocates in HBM */
+      pool = NULL;
+    }
+  }
+  {
+    gsize in_bytes = 0, out_bytes = 0;
+    GstStructure *config;
+    b200vf_element_unit_size (self->el, &in_bytes, &out_bytes);
+    if (size < out_bytes) size = (guint) out_bytes;
+    if (!pool) pool = gst_b200vf_buffer_pool_new (self->ctx);
+    config = gst_buffer_pool_get_config (pool);
+    gst_buffer_pool_config_set_params (config, outcaps, size, min, max);
+    gst_buffer_pool_config_add_option (config, GST_BUFFER_POOL_OPTION_VIDEO_META);
+    gst_buffer_pool_set_config (pool, config);
+  }
+  if (update_pool) gst_query_set_nth_allocation_pool (query, 0, pool, size, min, max);
+  else gst_query_add_allocation_pool (query, pool, size, min, max);
+  gst_object_unref (pool);
+  return TRUE;
 }
 
 /* ---- class / instance init, driven by the introspection table ---- */
@@ -287,6 +491,17 @@ b200vf_finalize (GObject * object)
   G_OBJECT_CLASS (g_type_class_peek_parent (G_OBJECT_GET_CLASS (object)))->finalize (object);
 }
 
+/* template caps: the reference's system-memory caps first (what an unchanged pipeline negotiates), then the same
+ * with the memory:B200VFMemory feature (sys/nvcodec/gstcudabasetransform.c:57-106 does the same for CUDAMemory) */
+static GstCaps *
+with_hbm_feature (GstCaps * caps)
+{
+  GstCaps *hbm = gst_caps_copy (caps);
+  gst_caps_set_features_simple (hbm, gst_caps_features_new (GST_CAPS_FEATURE_MEMORY_B200VF, NULL));
+  gst_caps_append (caps, hbm);
+  return caps;
+}
+
 static GstCaps *
 raw_caps_for (const b200vf_factory_info * fi)
 {
@@ -297,7 +512,7 @@ raw_caps_for (const b200vf_factory_info * fi)
   GstCaps *caps = gst_caps_from_string (c);
   g_free (c);
   g_string_free (s, TRUE);
-  return caps;
+  return with_hbm_feature (caps);
 }
 
 static void
@@ -322,8 +537,16 @@ b200vf_class_init (gpointer g_class, gpointer class_data)
     GParamFlags fl = G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS;
     b200vf_factory_property (fi.factory, i, &p);
     if (p.controllable) fl |= GST_PARAM_CONTROLLABLE;
-    /* perspective's "matrix" is a GValueArray of 9 doubles in the reference (gstperspective.c:222-232); the
-     * nine matrix-N doubles are installed too so that either spelling works */
+    if (!strncmp (p.name, "matrix-", 7)) {
+      /* perspective: the nine coefficients are ONE GObject property, "matrix", a GValueArray of doubles
+       * (gstperspective.c:222-233); installed once, under the id of matrix-0 */
+      if (!strcmp (p.name, "matrix-0"))
+        g_object_class_install_property (oc, PROP_FIRST + i, g_param_spec_value_array ("matrix", "Matrix",
+                "Matrix of dimension 3x3 to use in the 2D transform, passed as an array of 9 elements in row-major order",
+                g_param_spec_double ("Element", "Transformation matrix element", "Element of the transformation matrix",
+                    -G_MAXDOUBLE, G_MAXDOUBLE, 0.0, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS), fl));
+      continue;
+    }
     switch (p.type) {
       case B200VF_PROP_UINT: ps = g_param_spec_uint (p.name, p.name, p.name, (guint) p.min, (guint) p.max, (guint) p.def, fl); break;
       case B200VF_PROP_INT: ps = g_param_spec_int (p.name, p.name, p.name, (gint) p.min, (gint) p.max, (gint) p.def, fl); break;
@@ -336,8 +559,8 @@ b200vf_class_init (gpointer g_class, gpointer class_data)
 
   if (is_bayer_plugin_factory (fi.factory)) {
     GstCaps *raw = raw_caps_for (&fi);
-    GstCaps *bayer = gst_caps_from_string ("video/x-bayer,format=(string){bggr,grbg,gbrg,rggb},"
-        "width=(int)[1,MAX],height=(int)[1,MAX],framerate=(fraction)[0/1,MAX]");
+    GstCaps *bayer = with_hbm_feature (gst_caps_from_string ("video/x-bayer,format=(string){bggr,grbg,gbrg,rggb},"
+            "width=(int)[1,MAX],height=(int)[1,MAX],framerate=(fraction)[0/1,MAX]"));
     gboolean to_rgb = !strcmp (fi.factory, "bayer2rgb");
     gst_element_class_add_pad_template (ec, gst_pad_template_new ("src", GST_PAD_SRC, GST_PAD_ALWAYS, to_rgb ? raw : bayer));
     gst_element_class_add_pad_template (ec, gst_pad_template_new ("sink", GST_PAD_SINK, GST_PAD_ALWAYS, to_rgb ? bayer : raw));
@@ -354,9 +577,12 @@ b200vf_class_init (gpointer g_class, gpointer class_data)
     gst_element_class_add_pad_template (ec, gst_pad_template_new ("sink", GST_PAD_SINK, GST_PAD_ALWAYS, raw));
     gst_caps_unref (raw);
     vc->set_info = GST_DEBUG_FUNCPTR (b200vf_set_info);
-    if (fi.in_place) vc->transform_frame_ip = GST_DEBUG_FUNCPTR (b200vf_transform_frame_ip);
-    else vc->transform_frame = GST_DEBUG_FUNCPTR (b200vf_transform_frame);
+    /* (GstVideoFilter's class_init installed its own transform / transform_ip, which map to system memory first) */
+    if (fi.in_place) bc->transform_ip = GST_DEBUG_FUNCPTR (b200vf_vf_transform_ip);
+    else bc->transform = GST_DEBUG_FUNCPTR (b200vf_vf_transform);
   }
+  bc->propose_allocation = GST_DEBUG_FUNCPTR (b200vf_propose_allocation);
+  bc->decide_allocation = GST_DEBUG_FUNCPTR (b200vf_decide_allocation);
   bc->start = GST_DEBUG_FUNCPTR (b200vf_start);
   bc->stop = GST_DEBUG_FUNCPTR (b200vf_stop);
   bc->before_transform = GST_DEBUG_FUNCPTR (b200vf_before_transform);

@@ -739,6 +739,120 @@ B200VF_API int b200vf_element_transform (b200vf_element *e, b200vf_memory *in, b
   return rc ? rc : run (e, d_in, d_out, nframes, s);
 }
 
+// ---- frame layouts ------------------------------------------------------------------------------------------
+// transform_host assumes the default GstVideoInfo layout of the negotiated caps (what gst_video_info_set_format gives:
+// gst-plugins-base video-info.c fill_planes). A GstVideoFrame can carry a GstVideoMeta with other strides / plane
+// offsets (hardware decoders, some pools) and the reference elements honour GST_VIDEO_FRAME_PLANE_STRIDE / _PLANE_DATA
+// (gstcoloreffects.c:315-329, gstgeometrictransform.c:226-293, gstzebrastripe.c:219-243). The shells compare the frame's
+// layout with the default one and, when it differs, call transform_host_layout, which repacks by strided copies
+// (cudaMemcpy2DAsync per plane) between the caller's layout and the default layout in HBM.
+namespace {
+struct PlaneGeom { size_t offset; int stride, row_bytes, rows; };
+// planes of the default layout on the `side` (0 sink, 1 src) of element e; returns the plane count
+int default_planes (const b200vf_element *e, int side, PlaneGeom pl[4]) {
+  const int w = e->width, h = e->height;
+  const Kind k = e->def->kind;
+  if (k == K_BAYER2RGB || k == K_RGB2BAYER) {
+    const bool bayer_side = (k == K_BAYER2RGB) == (side == 0);
+    pl[0] = bayer_side ? PlaneGeom{ 0, round_up_4 (w), w, h } : PlaneGeom{ 0, 4 * w, 4 * w, h };
+    return 1;
+  }
+  if (!e->yuv) {                                               // packed RGB / AYUV / GRAY: one plane
+    pl[0] = { 0, e->in_stride, w * e->fmt->pstride, h };
+    return 1;
+  }
+  const char *f = e->yuv->name;
+  const int s0 = round_up (w, 4), h2 = round_up (h, 2);
+  if (!strcmp (f, "I420") || !strcmp (f, "YV12")) {
+    const int cw = round_up (w, 2) / 2, ch = h2 / 2, s1 = round_up (cw, 4);
+    pl[0] = { 0, s0, w, h };
+    pl[1] = { (size_t) s0 * h2, s1, cw, ch };
+    pl[2] = { (size_t) s0 * h2 + (size_t) s1 * ch, s1, cw, ch };
+    return 3;
+  }
+  if (!strcmp (f, "Y444")) {
+    for (int i = 0; i < 3; i++) pl[i] = { (size_t) i * s0 * h, s0, w, h };
+    return 3;
+  }
+  if (!strcmp (f, "Y42B")) {
+    const int cw = round_up (w, 2) / 2, s1 = round_up (w, 8) / 2;
+    pl[0] = { 0, s0, w, h };
+    pl[1] = { (size_t) s0 * h, s1, cw, h };
+    pl[2] = { (size_t) s0 * h + (size_t) s1 * h, s1, cw, h };
+    return 3;
+  }
+  if (!strcmp (f, "Y41B")) {
+    const int cw = round_up (w, 4) / 4, s1 = round_up (w, 16) / 4;
+    pl[0] = { 0, s0, w, h };
+    pl[1] = { (size_t) s0 * h, s1, cw, h };
+    pl[2] = { (size_t) s0 * h + (size_t) s1 * h, s1, cw, h };
+    return 3;
+  }
+  if (!strcmp (f, "NV12") || !strcmp (f, "NV21")) {
+    pl[0] = { 0, s0, w, h };
+    pl[1] = { (size_t) s0 * h2, s0, round_up (w, 2), h2 / 2 };
+    return 2;
+  }
+  pl[0] = { 0, e->in_stride, w * e->yuv->luma_ps, h };          // YUY2, UYVY, AYUV
+  return 1;
+}
+}  // namespace
+
+B200VF_API int b200vf_element_default_layout (const b200vf_element *e, int side, b200vf_frame_layout *out) {
+  B200VF_REQUIRE (e && out && (side == 0 || side == 1), B200VF_E_INVAL, "default_layout: bad argument");
+  B200VF_REQUIRE (e->negotiated, B200VF_E_NOT_NEGOTIATED, "%s: not negotiated yet", e->def->name);
+  PlaneGeom pl[4];
+  memset (out, 0, sizeof *out);
+  out->n_planes = default_planes (e, side, pl);
+  for (int i = 0; i < out->n_planes; i++) {
+    out->offset[i] = pl[i].offset; out->stride[i] = pl[i].stride; out->row_bytes[i] = pl[i].row_bytes; out->rows[i] = pl[i].rows;
+  }
+  return B200VF_OK;
+}
+
+B200VF_API int b200vf_element_transform_host_layout (b200vf_element *e, const void *h_in, const b200vf_frame_layout *in_layout,
+    void *h_out, const b200vf_frame_layout *out_layout)
+{
+  B200VF_REQUIRE (e && h_in && h_out, B200VF_E_INVAL, "transform: bad argument");
+  B200VF_REQUIRE (e->negotiated, B200VF_E_NOT_NEGOTIATED, "%s: not negotiated yet", e->def->name);
+  B200VF_REQUIRE (e->ctx, B200VF_E_NO_DEVICE, "%s: element has no device context (there is no CPU path)", e->def->name);
+  B200VF_CHECK_CUDA (cudaSetDevice (e->ctx->device));
+  int rc = ensure_staging (e);
+  if (rc) return rc;
+  if (e->def->kind == K_GEOMETRIC) {
+    rc = rebuild_index_if_needed (e, e->hs[0]);
+    if (rc) return rc;
+  }
+  PlaneGeom din[4], dout[4];
+  const int nin = default_planes (e, 0, din), nout = default_planes (e, 1, dout);
+  B200VF_REQUIRE (!in_layout || in_layout->n_planes == nin, B200VF_E_INVAL, "%s: input layout has %d planes, the format has %d",
+      e->def->name, in_layout ? in_layout->n_planes : 0, nin);
+  B200VF_REQUIRE (!out_layout || out_layout->n_planes == nout, B200VF_E_INVAL, "%s: output layout has %d planes, the format has %d",
+      e->def->name, out_layout ? out_layout->n_planes : 0, nout);
+  cudaStream_t s = e->hs[0];
+  for (int i = 0; i < nin; i++) {
+    const size_t off = in_layout ? in_layout->offset[i] : din[i].offset;
+    const int stride = in_layout ? in_layout->stride[i] : din[i].stride;
+    B200VF_REQUIRE (stride >= din[i].row_bytes, B200VF_E_INVAL, "%s: input plane %d stride %d < %d bytes per row", e->def->name, i, stride, din[i].row_bytes);
+    B200VF_CHECK_CUDA (cudaMemcpy2DAsync (e->d_in[0] + din[i].offset, din[i].stride, (const uint8_t *) h_in + off, stride,
+        din[i].row_bytes, din[i].rows, cudaMemcpyHostToDevice, s));
+  }
+  const bool in_place = h_in == h_out;
+  rc = run (e, e->d_in[0], in_place ? e->d_in[0] : e->d_out[0], 1, s);
+  if (rc) return rc;
+  const uint8_t *d_res = in_place ? e->d_in[0] : e->d_out[0];
+  for (int i = 0; i < nout; i++) {
+    const size_t off = out_layout ? out_layout->offset[i] : dout[i].offset;
+    const int stride = out_layout ? out_layout->stride[i] : dout[i].stride;
+    B200VF_REQUIRE (stride >= dout[i].row_bytes, B200VF_E_INVAL, "%s: output plane %d stride %d < %d bytes per row", e->def->name, i, stride, dout[i].row_bytes);
+    B200VF_CHECK_CUDA (cudaMemcpy2DAsync ((uint8_t *) h_out + off, stride, d_res + dout[i].offset, dout[i].stride, dout[i].row_bytes,
+        dout[i].rows, cudaMemcpyDeviceToHost, s));
+  }
+  B200VF_CHECK_CUDA (cudaStreamSynchronize (s));
+  if (e->def->kind == K_SCENECHANGE && e->last_events.size () > 1) e->last_events.resize (1);
+  return B200VF_OK;
+}
+
 // ---- pageable caller memory -------------------------------------------------------------------------------
 // A sysmem GstBuffer is pageable: cudaMemcpyAsync from / to it is staged through the driver's bounce buffer and runs
 // synchronously with the host. Buffers of a GstBufferPool recur, so the ranges seen are page-locked in place

@@ -435,6 +435,23 @@ int b200vf_element_unit_size (const b200vf_element *e, size_t *in_bytes, size_t 
 /* transform / transform_frame / transform_frame_ip on host memory: nframes
  * frames packed back to back; pipelined H2D / kernel / D2H; synchronous. */
 int b200vf_element_transform_host (b200vf_element *e, const void *h_in, void *h_out, int nframes);
+/* Frame layouts. transform_host assumes the default GstVideoInfo layout of the negotiated caps; a GstVideoFrame may
+ * carry other plane strides / offsets (GstVideoMeta), which the reference elements honour through
+ * GST_VIDEO_FRAME_PLANE_STRIDE / _PLANE_DATA (gstcoloreffects.c:315-329, gstgeometrictransform.c:226-293).
+ * b200vf_element_default_layout reports what transform_host assumes on the sink (side 0) / src (side 1) side;
+ * b200vf_element_transform_host_layout transforms ONE frame whose planes lie at `offset[i]` from h_in / h_out with
+ * `stride[i]` bytes per row (NULL layout = the default one; row_bytes / rows of the argument are ignored). In-place
+ * elements pass h_in == h_out and the same layout twice. */
+typedef struct b200vf_frame_layout {
+  int n_planes;
+  size_t offset[4];
+  int stride[4];
+  int row_bytes[4];             /* bytes of a row that carry samples */
+  int rows[4];
+} b200vf_frame_layout;
+int b200vf_element_default_layout (const b200vf_element *e, int side, b200vf_frame_layout *out);
+int b200vf_element_transform_host_layout (b200vf_element *e, const void *h_in, const b200vf_frame_layout *in_layout,
+    void *h_out, const b200vf_frame_layout *out_layout);
 /* How transform_host treats the caller's host buffers: 0 (default) as they are - pinned buffers copy asynchronously,
  * pageable ones through the driver's staging; 1 = pageable buffers that recur (what a sysmem GstBufferPool hands out):
  * each range is page-locked in place on first sight (cudaHostRegister) and remembered in an LRU cache of 64 ranges. */

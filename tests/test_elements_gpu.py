@@ -167,3 +167,59 @@ def test_chain_bayer_coloreffects_solarize_fused_equals_unfused(ctx, vf, orc, rn
         e2.set_property("preset", preset)
         out = e3.transform(e2.transform(e1.transform(src)))
         assert np.array_equal(out.reshape(h, 4 * w), want), preset
+
+
+def test_frames_with_foreign_strides_and_plane_offsets(ctx, vf, orc, rng):
+    """GstVideoMeta layouts (padded strides, moved planes): the reference elements honour GST_VIDEO_FRAME_PLANE_STRIDE /
+    _PLANE_DATA (gstcoloreffects.c:315-329, gstzebrastripe.c:219-243); transform_host_layout repacks into the default
+    layout in HBM and back. Same bytes as the default-layout call, padding untouched."""
+    w, h = 100, 37
+    # packed, in place: coloreffects on RGB (pstride 3) with rows padded to 512 bytes
+    e = ctx.element("coloreffects")
+    e.set_caps("RGB", "RGB", w, h)
+    e.set_property("preset", "sepia")
+    lay = e.default_layout(0)
+    assert (lay.n_planes, lay.stride[0], lay.row_bytes[0], lay.rows[0]) == (1, 300, 300, h)
+    fr = frames.random_u8(rng, h, 300)
+    want = e.transform(fr.copy()).reshape(h, 300)
+    big = rng.integers(0, 256, (h, 512), dtype=np.uint8)
+    big[:, :300] = fr
+    before = big.copy()
+    lay.stride[0] = 512
+    e.transform_layout(big, lay, big, lay)
+    assert np.array_equal(big[:, :300], want) and np.array_equal(big[:, 300:], before[:, 300:])
+    # planar, in place: zebrastripe on I420 with every plane moved and re-strided
+    z = ctx.element("zebrastripe")
+    z.set_caps("I420", "I420", w, h)
+    d = z.default_layout(0)
+    assert d.n_planes == 3 and d.stride[0] == 100 and d.stride[1] == 52 and d.offset[1] == 100 * 38
+    size = d.offset[2] + d.stride[2] * d.rows[2]
+    packed = rng.integers(0, 256, size, dtype=np.uint8)
+    z2 = ctx.element("zebrastripe")
+    z2.set_caps("I420", "I420", w, h)
+    want = z.transform(packed.copy())
+    moved = vf.FrameLayout()
+    moved.n_planes = 3
+    buf = rng.integers(0, 256, 40000, dtype=np.uint8)
+    pos = 64
+    for i in range(3):
+        moved.offset[i], moved.stride[i] = pos, d.stride[i] + 28
+        for r in range(d.rows[i]):
+            buf[pos + r * moved.stride[i]: pos + r * moved.stride[i] + d.row_bytes[i]] = packed[d.offset[i] + r * d.stride[i]: d.offset[i] + r * d.stride[i] + d.row_bytes[i]]
+        pos += moved.stride[i] * d.rows[i] + 128
+    z2.transform_layout(buf, moved, buf, moved)
+    for i in range(3):
+        for r in range(d.rows[i]):
+            got = buf[moved.offset[i] + r * moved.stride[i]: moved.offset[i] + r * moved.stride[i] + d.row_bytes[i]]
+            assert np.array_equal(got, want[d.offset[i] + r * d.stride[i]: d.offset[i] + r * d.stride[i] + d.row_bytes[i]]), (i, r)
+    # out of place with different layouts on both sides: bayer2rgb, mosaic rows padded to 256, RGBA rows to 1024
+    b = ctx.element("bayer2rgb")
+    b.set_caps("grbg", "RGBA", w, h)
+    src = frames.random_u8(rng, h, 100)
+    want = orc.bayer2rgb(src, w, h, "grbg", "RGBA")
+    sin = np.zeros((h, 256), np.uint8); sin[:, :100] = src
+    sout = np.full((h, 1024), 7, np.uint8)
+    li, lo = b.default_layout(0), b.default_layout(1)
+    li.stride[0], lo.stride[0] = 256, 1024
+    b.transform_layout(sin, li, sout, lo)
+    assert np.array_equal(sout[:, :400], want) and (sout[:, 400:] == 7).all()
