@@ -99,6 +99,8 @@ _SIGS = {
     "b200vf_coloreffects_ayuv": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _i, _i, _vp, _i, _vp]),
     "b200vf_chromahold": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200vf_gt_build_map": (_i, [C.c_char_p, _i, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_double), _i, _vp]),
+    "b200vf_gt_device_map_supported": (_i, [C.c_char_p]),
+    "b200vf_gt_build_index_device": (_i, [_vp, C.c_char_p, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "b200vf_gt_resolve_map": (_i, [_vp, _i, _i, _i, _vp]),
     "b200vf_remap": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _sz, _i, _u32, _vp]),
     "b200vf_gt_packed_bound": (_sz, [_i, _i]),
@@ -578,6 +580,20 @@ def gt_build_map(element, width, height, props=None):
     m = np.zeros((height, width, 2), np.float64)
     check(lib.b200vf_gt_build_map(element.encode(), width, height, cn, cv, n, _hptr(m)))
     return m
+
+
+def gt_device_map_supported(element):
+    return bool(lib.b200vf_gt_device_map_supported(element.encode()))
+
+
+def gt_build_index_device(ctx, element, width, height, props=None, off_edge=0, stream=None):
+    """the int32 gather table built on the GPU (mirror, square, stretch, bulge, tunnel, perspective); returns a DeviceBuffer"""
+    props = props or {}
+    names = (C.c_char_p * max(1, len(props)))(*[k.replace("_", "-").encode() for k in props])
+    vals = (C.c_double * max(1, len(props)))(*[float(v) for v in props.values()])
+    buf = DeviceBuffer(ctx, width * height * 4)
+    check(lib.b200vf_gt_build_index_device(ctx.h, element.encode(), width, height, names, vals, len(props), off_edge, buf.ptr, stream))
+    return buf
 
 
 def gt_resolve_map(map_xy, width, height, off_edge):

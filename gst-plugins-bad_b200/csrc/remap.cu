@@ -311,8 +311,12 @@ B200VF_API int b200vf_remap (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_d
   bool fast = pixel_stride == 4 && row_stride == 4 * width && ((uintptr_t) d_src) % 4 == 0 && ((uintptr_t) d_dst) % 4 == 0 &&
       ((uintptr_t) d_index) % 4 == 0 && frame_stride % 4 == 0;
   if (fast) {
-    int per_sm = 2;                                                      // measured sweep 1..8 (profiles/): 2 is best by 15 %
-    if (const char *e = getenv ("B200VF_REMAP_BLOCKS_PER_SM")) { int v = atoi (e); if (v >= 1 && v <= 8) per_sm = v; }   // tuning knob
+    // Blocks per SM over the WHOLE launch (grid.x * nframes) decide how much latency the dependent index -> gather ->
+    // store chain can hide: ~20 per SM measured best for a batch of 11 frames (2 per SM and frame, sweep 1..8 in
+    // profiles/); a single frame launched with 2 per SM left the SMs at 25 % occupancy and ran at 0.33 of the HBM
+    // peak (profiles/r02_remap.md), so few frames get more blocks each (8 resident blocks of 256 threads fill an SM).
+    int per_sm = nframes >= 8 ? 2 : nframes >= 4 ? 4 : 8;
+    if (const char *e = getenv ("B200VF_REMAP_BLOCKS_PER_SM")) { int v = atoi (e); if (v >= 1 && v <= 16) per_sm = v; }   // tuning knob
     int gx = ctx->sm_count * per_sm;
     size_t need = (npix + 1023) / 1024;                                  // 8 warps x 128 pixels per block and iteration
     if (need < (size_t) gx) gx = (int) need;

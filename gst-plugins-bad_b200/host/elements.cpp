@@ -256,8 +256,22 @@ int build_index (b200vf_element *e, const std::map<std::string, double> &P, cuda
     names.push_back (kv.first.c_str ());
     values.push_back (kv.second);
   }
+  int rc;
+  if (b200vf_gt_device_map_supported (e->def->name) && !getenv ("B200VF_GT_HOST_MAPS")) {
+    // maps without libm calls are evaluated on the GPU, bit-identically (csrc/gt_device_maps.cu): no host rebuild, no upload
+    if (e->index_px != npx) {
+      if (e->d_index) cudaFree (e->d_index);
+      e->d_index = nullptr;
+      e->index_px = 0;
+      rc = b200vf_malloc (e->ctx, npx * 4, (void **) &e->d_index);
+      if (rc) return rc;
+      e->index_px = npx;
+    }
+    return b200vf_gt_build_index_device (e->ctx, e->def->name, e->width, e->height, names.data (), values.data (), (int) names.size (),
+        off_edge, e->d_index, s);
+  }
   std::vector<double> map_xy (npx * 2);
-  int rc = b200vf_gt_build_map (e->def->name, e->width, e->height, names.data (), values.data (), (int) names.size (), map_xy.data ());
+  rc = b200vf_gt_build_map (e->def->name, e->width, e->height, names.data (), values.data (), (int) names.size (), map_xy.data ());
   if (rc) return rc;
   std::vector<int32_t> idx (npx);
   rc = b200vf_gt_resolve_map (map_xy.data (), e->width, e->height, off_edge, idx.data ());

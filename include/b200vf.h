@@ -273,6 +273,15 @@ int b200vf_chromahold (b200vf_ctx *ctx, uint8_t *d_data, int width, int height, 
 int b200vf_gt_build_map (const char *element, int width, int height, const char *const *prop_names,
     const double *prop_values, int nprops, double *map_xy /* [height][width][2] */);
 int b200vf_gt_resolve_map (const double *map_xy, int width, int height, int off_edge, int32_t *index_out);
+/* The same table built ON the GPU, for the maps whose arithmetic is +, -, *, /, sqrt and comparisons only (mirror,
+ * square, stretch, bulge, tunnel, perspective: b200vf_gt_device_map_supported): the kernel evaluates the reference's
+ * fp64 expressions operation for operation (compiled without FMA contraction) and applies do_map's policy and
+ * truncation, so d_index equals what b200vf_gt_build_map + b200vf_gt_resolve_map give - without the host rebuild
+ * (0.2 s at 8K) and the 132 MB upload every time a GstController moves a property (needs_remap,
+ * gstgeometrictransform.c:256-263). Maps that call libm stay on the host (B200VF_E_UNSUPPORTED here). */
+int b200vf_gt_device_map_supported (const char *element);
+int b200vf_gt_build_index_device (b200vf_ctx *ctx, const char *element, int width, int height,
+    const char *const *prop_names, const double *prop_values, int nprops, int off_edge, int32_t *d_index, void *stream);
 /* fill: 32-bit pattern the cleared frame holds (0, or 0x808010ff for AYUV =
  * GST_WRITE_UINT32_BE(0xff108080), :244-252); pixel_stride 1,2,3 or 4. */
 int b200vf_remap (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, const int32_t *d_index,

@@ -108,3 +108,62 @@ def test_packed_fisheye_4k_equals_plain(ctx, vf, rng):
     got, raw = gpu_remap_packed(ctx, vf, fr, idx, w, h)
     assert raw == 0
     assert np.array_equal(got, gpu_remap(ctx, vf, fr, idx, w, h, 4))
+
+
+DEVICE_MAPS = ("mirror", "square", "stretch", "bulge", "tunnel", "perspective")
+
+
+@pytest.mark.parametrize("element", DEVICE_MAPS)
+@pytest.mark.parametrize("w,h", [(64, 48), (100, 75), (257, 131)])
+def test_device_built_index_equals_host_table(ctx, vf, element, w, h):
+    """SURVEY 8f rank 3: the maps that need no libm are evaluated on the GPU in the reference's fp64 expression order;
+    the int32 table must equal, entry for entry, the one resolved on the host from the (reference-bit-equal) double
+    map - for every property set of the parity tests and every off-edge policy."""
+    import refprops
+    assert vf.gt_device_map_supported(element)
+    for props in refprops.CASES[element]:
+        m = vf.gt_build_map(element, w, h, props)
+        for name, off in OFF.items():
+            want = vf.gt_resolve_map(m, w, h, off)
+            d = vf.gt_build_index_device(ctx, element, w, h, props, off)
+            got = ctx.download(d, w * h * 4, dtype=np.int32).reshape(h, w)
+            assert np.array_equal(got, want.reshape(h, w)), (element, props, name, np.argwhere(got != want.reshape(h, w))[:5])
+    assert ctx.last_kernel() == "gt_index_device"
+
+
+def test_device_built_index_at_4k_and_8k(ctx, vf):
+    for (w, h) in [(3840, 2160), (7680, 4320)]:
+        for element, props in (("bulge", {"zoom": 7.5, "x_center": 0.3, "radius": 0.6}), ("square", {}), ("tunnel", {})):
+            want = vf.gt_resolve_map(vf.gt_build_map(element, w, h, props), w, h, 1)
+            got = ctx.download(vf.gt_build_index_device(ctx, element, w, h, props, 1), w * h * 4, dtype=np.int32)
+            assert np.array_equal(got, want.reshape(-1)), (element, w)
+
+
+def test_libm_maps_stay_on_the_host(ctx, vf):
+    for element in ("fisheye", "circle", "kaleidoscope", "pinch", "rotate", "sphere", "twirl", "waterripple", "marble"):
+        assert not vf.gt_device_map_supported(element)
+    with pytest.raises(vf.B200vfError) as err:
+        vf.gt_build_index_device(ctx, "twirl", 64, 48)
+    assert err.value.status == vf.E_UNSUPPORTED
+
+
+def test_element_rebuilds_its_table_on_the_gpu_when_a_property_moves(ctx, vf, orc, rng, monkeypatch):
+    """a GstController tick = set_property + next frame: the bulge element's table is rebuilt by one kernel
+    (no host map, no upload) and the frame equals the reference's; the host route gives the same bytes"""
+    w, h = 320, 200
+    fr = frames.random_u8(rng, h, 4 * w)
+    e = ctx.element("bulge")
+    e.set_caps("RGBA", "RGBA", w, h)
+    outs = []
+    for zoom in (3.0, 4.5, 9.0):
+        e.set_property("zoom", zoom)
+        l0 = ctx.launch_count()
+        outs.append(e.transform(fr).reshape(h, 4 * w))
+        assert ctx.launch_count() - l0 == 2                       # gt_index_device + remap4
+        want = orc.remap(fr, vf.gt_build_map("bulge", w, h, {"zoom": zoom}), w, h, 4, "clamp", False)
+        assert np.array_equal(outs[-1], want), zoom
+    monkeypatch.setenv("B200VF_GT_HOST_MAPS", "1")
+    e2 = ctx.element("bulge")
+    e2.set_caps("RGBA", "RGBA", w, h)
+    e2.set_property("zoom", 9.0)
+    assert np.array_equal(e2.transform(fr).reshape(h, 4 * w), outs[-1])
