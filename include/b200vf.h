@@ -294,10 +294,12 @@ int b200vf_remap (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, const i
  * table b200vf_gt_pack_index was given, and b200vf_remap_packed writes what
  * b200vf_remap writes. pack: host -> host buffer of b200vf_gt_packed_bound
  * bytes (*used = bytes to upload, *raw_chunks = 8-pixel chunks left uncoded);
- * width, height <= 32767. Measured (profiles/): at 8K fisheye the packed
- * table runs at 0.93x the int32 table's frame rate - the gather, not the
- * table, is the limiter - so the element mirror keeps the int32 table; the
- * packed form is for callers that hold many maps resident (2.7x smaller). */
+ * width, height <= 32767. Measured (profiles/r02_remap.md): in a BATCH of
+ * frames the int32 table is shared through L2 and the packed table runs at
+ * 0.93x its frame rate, so the element mirror keeps the int32 table; for
+ * single-frame launches the int32 table is read from HBM every frame (12 B/px
+ * moved for 8 B/px credited) and the packed form (9.5 B/px) is the better one,
+ * as it is for callers that hold many maps resident (2.7x smaller). */
 size_t b200vf_gt_packed_bound (int width, int height);
 int b200vf_gt_pack_index (const int32_t *index, int width, int height, void *packed, size_t capacity,
     size_t *used, size_t *raw_chunks);
