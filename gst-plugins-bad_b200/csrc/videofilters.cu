@@ -14,6 +14,7 @@
 // instruction with the SIMD-in-word video instructions (vcmpgeu4 / vabsdiffu4 / vsadu4). Rows whose base or pitch
 // is not 16-byte aligned take the same code on 32-bit words; the last width % 4 samples of a row are done bytewise.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -283,6 +284,131 @@ smooth_kernel (const uint8_t *src, int src_stride, size_t src_fs, uint8_t *dst, 
   }
 }
 
+// The same filter with four window samples per instruction (round 2; the scalar kernel above spends its time in 63
+// LDS.U8 + compare + add chains per sample: 0.01 of the HBM peak). A thread owns the 4 output pixels of one aligned
+// 32-bit word. The tile is kept in shared memory in FOUR byte-shifted copies (copy s, word i = bytes 4i+s .. 4i+s+3 of
+// the row), so that any 4-byte group of window samples, at any byte offset, is ONE aligned LDS.32 - no funnel shifts on
+// the ALU pipe, which is the half-rate pipe that bounds this kernel (ncu: alu 83 %, issue 82 %). A group then costs
+//   VABSDIFF4          |sample - ref| per byte (ref replicated in the four lanes)
+//   LOP3, IADD, LOP3   per-byte unsigned "< tolerance" without cross-byte carries, flag in bit 7 of each byte; lanes
+//                      outside the window / the frame carry a threshold of 0 and never pass
+//   IDP.4A x 2         sum += samples . flags and count += 1 . flags (both scaled by 128: the flags are 0x80)
+// i.e. ~2 instructions per sample instead of ~6. MODE 0: tolerance <= 128 (the default is 8): a < t per byte is bit 7 of
+// ((t + 127) - (a & 127)) & ~a, no carry can cross a byte; MODE 1: any tolerance <= 255 (one more LOP3); MODE 2:
+// |tolerance| >= 256 admits every sample of the window. The final sum / count (count <= 196, sum < 2^16) is
+// floor ((sum + 0.5) * rcp (count)) in fp32: the +0.5 keeps the approximate reciprocal's error (<= 2 ulp) away from
+// every integer boundary (the nearest one is 0.5 / count >= 1.5e-3 away) - checked against integer division for every
+// (count, sum) and every reciprocal within +-3 ulp in tests/test_host_logic_cpu.py::test_smooth_division_trick_is_exact.
+// The window geometry is the scalar kernel's (smooth_rows; the reference's quirks are listed there).
+// floor (total / num) for num in [1, 324], total <= 255 * num (see the kernel comment): one MUFU.RCP (rcp.approx, within
+// 2 ulp of 1 / num) instead of the ~20 instructions and branches of an exact reciprocal or an integer division
+__device__ __forceinline__ uint32_t smooth_div (uint32_t total, uint32_t num) {
+  float r;
+  asm ("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float) num));
+  return (uint32_t) (((float) total + 0.5f) * r);
+}
+
+template <int FS> struct SmoothGeom {
+  static constexpr int HW = (FS + 3) / 4;                      // halo words each side of the thread's own word
+  static constexpr int NW = (2 * FS + 1 + 3) / 4;              // 4-sample groups per pixel and window row
+};
+constexpr int SMD_TWW = 32, SMD_TH = 32;                       // tile: 32 words (128 pixels) x 32 rows, 256 threads x 4 rows
+
+template <int FS, int MODE>
+__global__ void __launch_bounds__ (256)
+smooth_dp4a_kernel (const uint8_t *src, int src_stride, size_t src_fs, uint8_t *dst, int dst_stride, size_t dst_fs,
+    int width, int height, int atol /* 0 .. 256 */)
+{
+  typedef SmoothGeom<FS> G;
+  constexpr int TROWS = SMD_TH + 2 * FS + 2, TWORDS = SMD_TWW + 2 * G::HW + 1;
+  extern __shared__ uint32_t smooth_tile[];                    // [4 shifts][TROWS][TWORDS]
+  uint32_t (*tile)[TROWS][TWORDS] = reinterpret_cast<uint32_t (*)[TROWS][TWORDS]> (smooth_tile);
+  const uint8_t *s = src + (size_t) blockIdx.z * src_fs;
+  uint8_t *d = dst + (size_t) blockIdx.z * dst_fs;
+  const int xw0 = blockIdx.x * SMD_TWW, r0 = blockIdx.y * SMD_TH;       // first word column / first row of the tile
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int nwords = (width + 3) >> 2;                                   // words that hold samples (the last one possibly partly)
+  for (int i = tid; i < TROWS * TWORDS; i += 256) {                     // rows r0-FS .., word columns xw0-HW ..
+    const int tr = i / TWORDS, tc = i % TWORDS;
+    const int gr = r0 - FS + tr, gw = xw0 - G::HW + tc;
+    uint32_t v = 0, n = 0;
+    if (gr >= 0 && gr < height) {
+      if (gw >= 0 && gw < nwords) v = ldg_u32 (s + (size_t) gr * src_stride + 4 * gw);
+      if (gw + 1 >= 0 && gw + 1 < nwords) n = ldg_u32 (s + (size_t) gr * src_stride + 4 * (gw + 1));
+    }
+    tile[0][tr][tc] = v;
+    tile[1][tr][tc] = __funnelshift_r (v, n, 8);
+    tile[2][tr][tc] = __funnelshift_r (v, n, 16);
+    tile[3][tr][tc] = __funnelshift_r (v, n, 24);
+  }
+  __syncthreads ();
+  const int xw = xw0 + threadIdx.x, x0 = 4 * xw;
+  if (x0 >= width) return;
+  // per pixel p and group k: the threshold word - the tolerance in the lanes whose column lies in the pixel's window
+  // [x - FS, x + FS] and in the frame, 0 elsewhere (a lane with threshold 0 never passes). MODE 0 stores t + 127 per
+  // byte, MODE 2 the flag itself.
+  uint32_t thr[4][G::NW];
+  const uint32_t at = MODE == 2 ? 0x80u : MODE == 0 ? (uint32_t) atol + 127u : (uint32_t) atol;
+#pragma unroll
+  for (int p = 0; p < 4; p++)
+#pragma unroll
+    for (int k = 0; k < G::NW; k++) {
+      uint32_t t = MODE == 0 ? 0x7f7f7f7fu : 0u;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int c = -FS + 4 * k + j, col = x0 + p + c;
+        if (c <= FS && col >= 0 && col < width) t = (t & ~(0xffu << (8 * j))) | (at << (8 * j));
+      }
+      thr[p][k] = t;
+    }
+  const int last = height >= 2 ? height - 2 : 0;                         // last row the reference writes
+#pragma unroll 1
+  for (int q = 0; q < SMD_TH / 8; q++) {
+    const int r = r0 + threadIdx.y * (SMD_TH / 8) + q;
+    if (r > last) break;
+    int ra, rb;
+    smooth_rows (height >= 2 ? r + 1 : 0, height, FS, &ra, &rb);
+    const uint32_t refw = tile[0][r - r0 + FS][threadIdx.x + G::HW];
+    uint32_t ref4[4];
+    uint32_t sum[4] = { 0, 0, 0, 0 }, cnt[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int p = 0; p < 4; p++) ref4[p] = ((refw >> (8 * p)) & 0xffu) * 0x01010101u;
+#pragma unroll 1
+    for (int wr = ra; wr < rb; wr++) {
+      const int tr = wr - r0 + FS;
+#pragma unroll
+      for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int k = 0; k < G::NW; k++) {
+          constexpr int B0 = 4 * G::HW - FS;                             // first byte of pixel 0's window, counted from the thread's word 0
+          const int b = p + B0 + 4 * k;                                  // compile-time after unrolling
+          const uint32_t v = tile[b & 3][tr][threadIdx.x + (b >> 2)];
+          uint32_t f;
+          if (MODE == 2) f = thr[p][k];
+          else {
+            const uint32_t a = __vabsdiffu4 (v, ref4[p]);
+            if (MODE == 0) f = (thr[p][k] - (a & 0x7f7f7f7fu)) & ~a & 0x80808080u;
+            else {
+              const uint32_t t = thr[p][k], h = (~a & 0x7f7f7f7fu) + (t & 0x7f7f7f7fu);
+              f = ((~a & t) | (~(a ^ t) & h)) & 0x80808080u;
+            }
+          }
+          sum[p] = __dp4a (v, f, sum[p]);
+          cnt[p] = __dp4a (0x01010101u, f, cnt[p]);
+        }
+    }
+    uint32_t out = 0;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      const uint32_t total = (sum[p] >> 7) + (ref4[p] & 0xffu), num = (cnt[p] >> 7) + 1u;
+      out |= smooth_div (total, num) << (8 * p);
+    }
+    uint8_t *o = d + (size_t) r * dst_stride + x0;
+    if (x0 + 4 <= width) *reinterpret_cast<uint32_t *> (o) = out;
+    else for (int p = 0; x0 + p < width; p++) o[p] = (uint8_t) (out >> (8 * p));
+  }
+}
+
 // ---- videoanalyse (gst/videosignal/gstvideoanalyse.c:206-236) --------------------------------------------
 // The reference walks the luma plane twice: sum, then sum of (avg - d)^2 with avg = sum / (w*h) in int. The second
 // sum is an exact integer identity of the first two moments, N*avg^2 - 2*avg*sum + sum(d^2), so one pass that
@@ -435,6 +561,24 @@ B200VF_API int b200vf_smooth_plane (b200vf_ctx *ctx, const uint8_t *d_src, int s
   const int atol = at > 256 ? 256 : (int) at;
   // a negative filter-size leaves the window empty (fx1 >= fx2 in the reference's loop): the output is the reference sample
   const int fs = filtersize < 0 ? 0 : filtersize;
+  // four samples per instruction when the rows are word-aligned and the window fits the packed counters
+  const bool packed = filtersize >= 0 && filtersize <= 6 && src_stride % 4 == 0 && dst_stride % 4 == 0 && ((uintptr_t) d_src) % 4 == 0 &&
+      ((uintptr_t) d_dst) % 4 == 0 && src_frame_stride % 4 == 0 && dst_frame_stride % 4 == 0 && !getenv ("B200VF_SMOOTH_SCALAR");
+  if (packed) {
+    const dim3 blk (32, 8), grd ((width + 4 * SMD_TWW - 1) / (4 * SMD_TWW), (height + SMD_TH - 1) / SMD_TH, nframes);
+    B200VF_REQUIRE (grd.y <= 65535, B200VF_E_UNSUPPORTED, "smooth: grid limits");
+    const int mode = atol > 255 ? 2 : atol <= 128 ? 0 : 1;
+#define SMOOTH_LAUNCH(F, M) { \
+      const int smem = 4 * (SMD_TH + 2 * F + 2) * (SMD_TWW + 2 * SmoothGeom<F>::HW + 1) * 4; \
+      int rcs = b200vf_func_smem (ctx, (const void *) smooth_dp4a_kernel<F, M>, smem); \
+      if (rcs) return rcs; \
+      smooth_dp4a_kernel<F, M><<<grd, blk, smem, s>>> (d_src, src_stride, src_frame_stride, d_dst, dst_stride, dst_frame_stride, width, height, atol); }
+#define SMOOTH_CASE(F) case F: if (mode == 0) SMOOTH_LAUNCH (F, 0) else if (mode == 1) SMOOTH_LAUNCH (F, 1) else SMOOTH_LAUNCH (F, 2) break;
+    switch (fs) { SMOOTH_CASE (0) SMOOTH_CASE (1) SMOOTH_CASE (2) SMOOTH_CASE (3) SMOOTH_CASE (4) SMOOTH_CASE (5) default: SMOOTH_CASE (6) }
+#undef SMOOTH_CASE
+#undef SMOOTH_LAUNCH
+    return b200vf_launched (ctx, "smooth_dp4a");
+  }
   const dim3 block (64, 4), grid ((width + SM_TW - 1) / SM_TW, (height + SM_TH - 1) / SM_TH, nframes);
   smooth_kernel<<<grid, block, 0, s>>> (d_src, src_stride, src_frame_stride, d_dst, dst_stride, dst_frame_stride, width, height, atol, fs,
       filtersize < 0 ? 1 : 0);

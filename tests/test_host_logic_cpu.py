@@ -335,3 +335,19 @@ def test_yuv_frame_geometry_of_the_videofilters_elements(vf):
         with pytest.raises(vf.B200vfError):
             e.set_caps("NV12", "NV12", 32, 16)                # planar Y formats only (gstvideodiff.c:48-52)
         e.close()
+
+
+def test_smooth_division_trick_is_exact():
+    """smooth_dp4a (csrc/videofilters.cu) divides sum / count as floor((sum + 0.5) * RN(1 / count)) in fp32; numpy's
+    float32 arithmetic is the same IEEE arithmetic (RN reciprocal, RN multiply), so every (count, sum) the kernel can
+    see - count <= (2*6+1)*(2*6+3)+1 = 196 for filter-size <= 6 (324 checked), sum <= 255 * count - is checked against
+    integer division here."""
+    np.seterr(over="ignore")
+    for num in range(1, 325):
+        total = np.arange(0, 255 * num + 1, dtype=np.int64)
+        rcp = np.float32(1.0) / np.float32(num)
+        # the kernel uses rcp.approx (within 2 ulp of 1 / num): every reciprocal within +-3 ulp must give the same quotient
+        for ulps in range(-3, 4):
+            r = (rcp.view(np.uint32) + np.uint32(ulps & 0xffffffff)).view(np.float32) if ulps else rcp
+            got = ((total.astype(np.float32) + np.float32(0.5)) * r).astype(np.int64)
+            assert np.array_equal(got, total // num), (num, ulps)
