@@ -113,6 +113,9 @@ _SIGS = {
     "b200vf_sad_u8": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _vp, _vp]),
     "b200vf_luma_moments": (_i, [_vp, _vp, _i, _sz, _i, _i, _i, _vp, _vp]),
     "b200vf_videoanalyse_finish": (_i, [C.c_uint64, C.c_uint64, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "b200vf_videomark_draw": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _i, _vp, C.c_uint64, _vp]),
+    "b200vf_videomark_box_sums": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _i, _vp, _vp, C.POINTER(_i), _vp]),
+    "b200vf_videomark_detect_decide": (_i, [_vp, _i, _i, _i, _i, _vp, C.c_double, C.c_double, C.POINTER(_i), C.POINTER(_i), C.POINTER(C.c_uint64)]),
     "b200vf_smooth_plane": (_i, [_vp, _vp, _i, _sz, _vp, _i, _sz, _i, _i, _i, _i, _i, _vp]),
     "b200vf_scenechange_reset": (_i, [_vp]),
     "b200vf_scenechange_update": (_i, [_vp, C.c_double, C.POINTER(_i)]),
@@ -143,6 +146,7 @@ _SIGS = {
     "b200vf_element_unit_size": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "b200vf_element_transform_host": (_i, [_vp, _vp, _vp, _i]),
     "b200vf_element_transform_device": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "b200vf_element_last_values": (_i, [_vp, _vp, _i]),
     "b200vf_element_last_events": (_i, [_vp, _vp, _i]),
 }
 
@@ -346,6 +350,22 @@ class Context:
     def luma_moments(self, luma, stride, width, height, sums, nframes=1, frame_stride=None, stream=None):
         fs = frame_stride if frame_stride is not None else stride * height
         check(lib.b200vf_luma_moments(self.h, _ptr(luma), stride, fs, width, height, nframes, _ptr(sums), stream))
+
+    def videomark_draw(self, luma, pixel_stride, row_stride, width, height, params, pattern_data=10, nframes=1, frame_stride=None, stream=None):
+        fs = frame_stride if frame_stride is not None else row_stride * height
+        check(lib.b200vf_videomark_draw(self.h, _ptr(luma), pixel_stride, row_stride, fs, nframes, width, height, C.byref(params),
+                                        pattern_data, stream))
+
+    def videomark_box_sums(self, luma, pixel_stride, row_stride, width, height, params, nframes=1, frame_stride=None, stream=None):
+        """-> uint64 array [nframes, n_boxes]"""
+        fs = frame_stride if frame_stride is not None else row_stride * height
+        d = DeviceBuffer(self, nframes * VIDEOMARK_MAX_BOXES * 8)
+        n = C.c_int(0)
+        check(lib.b200vf_videomark_box_sums(self.h, _ptr(luma), pixel_stride, row_stride, fs, nframes, width, height, C.byref(params),
+                                            d.ptr, C.byref(n), stream))
+        out = self.download(d, dtype=np.uint64, stream=stream).reshape(nframes, VIDEOMARK_MAX_BOXES)[:, :n.value]
+        d.free()
+        return out
 
     def smooth_plane(self, src, dst, stride, width, height, tolerance=8, filtersize=3, nframes=1, frame_stride=None, stream=None):
         fs = frame_stride if frame_stride is not None else stride * height
@@ -670,6 +690,26 @@ def shard_rows(height, rank, nranks):
     return r0.value, r.value
 
 
+VIDEOMARK_MAX_BOXES = 128
+
+
+class VideoMarkParams(C.Structure):
+    _fields_ = [("pattern_width", C.c_int), ("pattern_height", C.c_int), ("pattern_count", C.c_int), ("pattern_data_count", C.c_int),
+                ("left_offset", C.c_int), ("bottom_offset", C.c_int)]
+
+    def __init__(self, pattern_width=4, pattern_height=16, pattern_count=4, pattern_data_count=5, left_offset=0, bottom_offset=0):
+        super().__init__(pattern_width, pattern_height, pattern_count, pattern_data_count, left_offset, bottom_offset)
+
+
+def videomark_detect_decide(params, width, height, row_stride, pixel_stride, sums, center=0.5, sensitivity=0.3, in_pattern=False):
+    """-> (in_pattern, message posted, data)"""
+    sm = np.ascontiguousarray(sums, np.uint64)
+    ip, msg, data = C.c_int(int(in_pattern)), C.c_int(0), C.c_uint64(0)
+    check(lib.b200vf_videomark_detect_decide(C.byref(params), width, height, row_stride, pixel_stride, _hptr(sm), center, sensitivity,
+                                             C.byref(ip), C.byref(msg), C.byref(data)))
+    return bool(ip.value), bool(msg.value), int(data.value)
+
+
 class FrameLayout(C.Structure):
     _fields_ = [("n_planes", C.c_int), ("offset", C.c_size_t * 4), ("stride", C.c_int * 4), ("row_bytes", C.c_int * 4),
                 ("rows", C.c_int * 4)]
@@ -776,6 +816,13 @@ class Element:
 
     def transform_device(self, d_in, d_out, nframes=1, stream=None):
         check(lib.b200vf_element_transform_device(self.h, _ptr(d_in), _ptr(d_out), nframes, stream))
+
+    def last_values(self):
+        v = (C.c_double * 8)()
+        n = lib.b200vf_element_last_values(self.h, v, 8)
+        if n < 0:
+            check(n)
+        return [v[i] for i in range(n)]
 
     def last_events(self):
         """scenechange: per frame of the last transform call, True where the reference pushes its force-key-unit event"""

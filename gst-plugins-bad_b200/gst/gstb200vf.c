@@ -1,7 +1,7 @@
 /* gstb200vf.c - GStreamer element shells over libb200vf.so (C/GLib, no per-pixel work).
  *
  * One source, compiled once per plugin with
- * -DB200VF_PLUGIN=<bayer|gaudieffects|coloreffects|geometrictransform|videofiltersbad>
+ * -DB200VF_PLUGIN=<bayer|gaudieffects|coloreffects|geometrictransform|videofiltersbad|smooth|videosignal>
  * (gst/meson.build), yields libgstbayer.so, libgstgaudieffects.so, libgstcoloreffects.so,
  * libgstgeometrictransform.so and libgstvideofiltersbad.so (zebrastripe, videodiff, scenechange) that REPLACE the stock plugins: same plugin names, factory names, GType names and
  * parents, klass/description strings, GObject properties (names, ranges, defaults, GST_PARAM_CONTROLLABLE) and pad
@@ -104,6 +104,7 @@ b200vf_set_property (GObject * object, guint id, const GValue * value, GParamSpe
     return;
   }
   if (G_VALUE_HOLDS_UINT (value)) v = g_value_get_uint (value);
+  else if (G_VALUE_HOLDS_UINT64 (value)) v = (gdouble) g_value_get_uint64 (value);
   else if (G_VALUE_HOLDS_INT (value)) v = g_value_get_int (value);
   else if (G_VALUE_HOLDS_BOOLEAN (value)) v = g_value_get_boolean (value);
   else if (G_VALUE_HOLDS_DOUBLE (value)) v = g_value_get_double (value);
@@ -136,6 +137,7 @@ b200vf_get_property (GObject * object, guint id, GValue * value, GParamSpec * ps
   }
   b200vf_element_get_property (self->el, pspec->name, &v);
   if (G_VALUE_HOLDS_UINT (value)) g_value_set_uint (value, (guint) v);
+  else if (G_VALUE_HOLDS_UINT64 (value)) g_value_set_uint64 (value, (guint64) v);
   else if (G_VALUE_HOLDS_INT (value)) g_value_set_int (value, (gint) v);
   else if (G_VALUE_HOLDS_BOOLEAN (value)) g_value_set_boolean (value, v != 0);
   else if (G_VALUE_HOLDS_DOUBLE (value)) g_value_set_double (value, v);
@@ -308,6 +310,36 @@ push_scenechange_event (GstB200vf * self, GstBuffer * buf)
             GST_CLOCK_TIME_NONE, FALSE, self->key_unit_count++));
 }
 
+/* videoanalyse / simplevideomarkdetect report through element messages (gstvideoanalyse.c:178-204,
+ * gstsimplevideomarkdetect.c:352-389); the numbers come back from the library (b200vf_element_last_values) */
+static void
+post_analysis_message (GstB200vf * self, GstBuffer * buf)
+{
+  GstBaseTransform *trans = GST_BASE_TRANSFORM (self);
+  const gchar *factory = B200VF_GET_CLASS (self)->factory;
+  gboolean analyse = !strcmp (factory, "videoanalyse"), detect = !strcmp (factory, "simplevideomarkdetect");
+  gdouble v[3] = { 0, 0, 0 }, want_message = 1;
+  guint64 duration, timestamp, running_time, stream_time;
+  GstStructure *st;
+  if (!analyse && !detect) return;
+  b200vf_element_get_property (self->el, "message", &want_message);
+  if (want_message == 0 || b200vf_element_last_values (self->el, v, 3) < 2) return;
+  if (detect && v[0] == 0) return;                /* the detector posts only when a pattern appears, changes or disappears */
+  timestamp = GST_BUFFER_TIMESTAMP (buf);
+  duration = GST_BUFFER_DURATION (buf);
+  running_time = gst_segment_to_running_time (&trans->segment, GST_FORMAT_TIME, timestamp);
+  stream_time = gst_segment_to_stream_time (&trans->segment, GST_FORMAT_TIME, timestamp);
+  if (analyse)
+    st = gst_structure_new ("GstVideoAnalyse", "timestamp", G_TYPE_UINT64, timestamp, "stream-time", G_TYPE_UINT64, stream_time,
+        "running-time", G_TYPE_UINT64, running_time, "duration", G_TYPE_UINT64, duration, "luma-average", G_TYPE_DOUBLE, v[0],
+        "luma-variance", G_TYPE_DOUBLE, v[1], NULL);
+  else
+    st = gst_structure_new ("GstSimpleVideoMarkDetect", "have-pattern", G_TYPE_BOOLEAN, v[1] != 0, "timestamp", G_TYPE_UINT64, timestamp,
+        "stream-time", G_TYPE_UINT64, stream_time, "running-time", G_TYPE_UINT64, running_time, "duration", G_TYPE_UINT64, duration,
+        "data", G_TYPE_UINT64, (guint64) v[2], NULL);
+  gst_element_post_message (GST_ELEMENT_CAST (self), gst_message_new_element (GST_OBJECT_CAST (self), st));
+}
+
 /* GstVideoFilter elements: GstBaseTransform::transform / transform_ip are overridden (instead of transform_frame[_ip])
  * because GstVideoFilter maps both buffers to system memory before it calls transform_frame - for buffers of the HBM
  * pool that would download every frame. */
@@ -369,7 +401,10 @@ b200vf_vf_transform_ip (GstBaseTransform * base, GstBuffer * buf)
     gst_video_frame_unmap (&frame);
     ret = b200vf_flow (self, rc);
   }
-  if (ret == GST_FLOW_OK) push_scenechange_event (self, buf);
+  if (ret == GST_FLOW_OK) {
+    push_scenechange_event (self, buf);
+    post_analysis_message (self, buf);
+  }
   return ret;
 }
 
@@ -552,6 +587,7 @@ b200vf_class_init (gpointer g_class, gpointer class_data)
       case B200VF_PROP_INT: ps = g_param_spec_int (p.name, p.name, p.name, (gint) p.min, (gint) p.max, (gint) p.def, fl); break;
       case B200VF_PROP_BOOL: ps = g_param_spec_boolean (p.name, p.name, p.name, p.def != 0, fl); break;
       case B200VF_PROP_DOUBLE: ps = g_param_spec_double (p.name, p.name, p.name, p.min, p.max, p.def, fl); break;
+      case B200VF_PROP_UINT64: ps = g_param_spec_uint64 (p.name, p.name, p.name, 0, G_MAXUINT64, (guint64) p.def, fl); break;
       case B200VF_PROP_ENUM: ps = g_param_spec_enum (p.name, p.name, p.name, enum_type_for (fi.type_name, &p), (gint) p.def, fl); break;
     }
     g_object_class_install_property (oc, PROP_FIRST + i, ps);

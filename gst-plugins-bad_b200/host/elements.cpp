@@ -24,7 +24,8 @@
 namespace {
 
 enum Kind { K_BAYER2RGB, K_RGB2BAYER, K_BURN, K_CHROMIUM, K_DILATE, K_DODGE, K_EXCLUSION, K_GAUSSBLUR, K_SOLARIZE,
-  K_COLOREFFECTS, K_CHROMAHOLD, K_GEOMETRIC, K_ZEBRASTRIPE, K_VIDEODIFF, K_SCENECHANGE, K_SMOOTH };
+  K_COLOREFFECTS, K_CHROMAHOLD, K_GEOMETRIC, K_ZEBRASTRIPE, K_VIDEODIFF, K_SCENECHANGE, K_SMOOTH, K_VIDEOANALYSE, K_VIDEOMARK,
+  K_VIDEOMARKDETECT };
 
 struct FormatDef { const char *name; int pstride; int off[4]; /* R,G,B,A (or Y,U,V,A) poffsets; -1 = none */ };
 // gst-plugins-base video-format.c packed layouts (byte offsets in memory)
@@ -42,7 +43,7 @@ const char *kBayerFormats[] = { "bggr", "gbrg", "grbg", "rggb" };   // enum orde
 struct YuvDef { const char *name; int luma_off, luma_ps; };
 const YuvDef kYuvFormats[] = {
   { "I420", 0, 1 }, { "YV12", 0, 1 }, { "Y444", 0, 1 }, { "Y42B", 0, 1 }, { "Y41B", 0, 1 }, { "NV12", 0, 1 }, { "NV21", 0, 1 },
-  { "YUY2", 0, 2 }, { "UYVY", 1, 2 }, { "AYUV", 1, 4 },
+  { "YUY2", 0, 2 }, { "UYVY", 1, 2 }, { "AYUV", 1, 4 }, { "YVYU", 0, 2 },
 };
 const YuvDef *find_yuv (const char *n) {
   for (const auto &f : kYuvFormats) if (!strcmp (f.name, n)) return &f;
@@ -58,7 +59,7 @@ void yuv_geometry (const char *fmt, int w, int h, int *stride0, size_t *size) {
   else if (!strcmp (fmt, "Y42B")) *size = ((size_t) s0 + round_up (w, 8)) * h;
   else if (!strcmp (fmt, "Y41B")) *size = ((size_t) s0 + round_up (w, 16) / 2) * h;
   else if (!strcmp (fmt, "NV12") || !strcmp (fmt, "NV21")) *size = (size_t) s0 * h2 + (size_t) s0 * (h2 / 2);
-  else if (!strcmp (fmt, "YUY2") || !strcmp (fmt, "UYVY")) { *stride0 = round_up (w * 2, 4); *size = (size_t) *stride0 * h; }
+  else if (!strcmp (fmt, "YUY2") || !strcmp (fmt, "UYVY") || !strcmp (fmt, "YVYU")) { *stride0 = round_up (w * 2, 4); *size = (size_t) *stride0 * h; }
   else { *stride0 = w * 4; *size = (size_t) w * 4 * h; }     // AYUV
 }
 
@@ -71,7 +72,7 @@ int find_bayer (const char *n) {
   return -1;
 }
 
-enum PType { P_UINT, P_INT, P_BOOL, P_DOUBLE, P_ENUM };
+enum PType { P_UINT, P_INT, P_BOOL, P_DOUBLE, P_ENUM, P_UINT64 };
 struct PropDef {
   const char *name; PType type; double lo, hi, def; std::vector<const char *> nicks;
   bool ctl = true;
@@ -160,6 +161,20 @@ const std::vector<FactoryDef> &factories () {
       { { "threshold", P_INT, 0, 100, 90, {}, false } }, false, 0 },           // gstzebrastripe.c:81-82,126-130
     { "videodiff", K_VIDEODIFF, { "I420", "Y444", "Y42B", "Y41B" }, {}, false, 0 },                  // gstvideodiff.c:48-52
     { "scenechange", K_SCENECHANGE, { "I420", "Y42B", "Y41B", "Y444" }, {}, false, 0 },              // gstscenechange.c:103-104
+    // videosignal (gst/videosignal/gstvideosignal.c): videoanalyse (gstvideoanalyse.c:49-60,96-100), simplevideomark
+    // (gstsimplevideomark.c:87-100,136-182), simplevideomarkdetect (gstsimplevideomarkdetect.c:107-118,160-208)
+    { "videoanalyse", K_VIDEOANALYSE, { "I420", "YV12", "Y444", "Y42B", "Y41B" }, { { "message", P_BOOL, 0, 1, 1, {}, false } }, false, 0 },
+    { "simplevideomark", K_VIDEOMARK, { "I420", "YV12", "Y41B", "Y42B", "Y444", "YUY2", "UYVY", "AYUV", "YVYU" },
+      { { "pattern-width", P_INT, 1, 2147483647.0, 4, {}, false }, { "pattern-height", P_INT, 1, 2147483647.0, 16, {}, false },
+        { "pattern-count", P_INT, 0, 2147483647.0, 4, {}, false }, { "pattern-data-count", P_INT, 0, 64, 5, {}, false },
+        { "pattern-data", P_UINT64, 0, 18446744073709551615.0, 10, {}, false }, { "enabled", P_BOOL, 0, 1, 1, {}, false },
+        { "left-offset", P_INT, 0, 2147483647.0, 0, {}, false }, { "bottom-offset", P_INT, 0, 2147483647.0, 0, {}, false } }, false, 0 },
+    { "simplevideomarkdetect", K_VIDEOMARKDETECT, { "I420", "YV12", "Y41B", "Y42B", "Y444", "YUY2", "UYVY", "AYUV", "YVYU" },
+      { { "message", P_BOOL, 0, 1, 1, {}, false }, { "pattern-width", P_INT, 1, 2147483647.0, 4, {}, false },
+        { "pattern-height", P_INT, 1, 2147483647.0, 16, {}, false }, { "pattern-count", P_INT, 0, 2147483647.0, 4, {}, false },
+        { "pattern-data-count", P_INT, 0, 2147483647.0, 5, {}, false }, { "pattern-center", P_DOUBLE, 0.0, 1.0, 0.5, {}, false },
+        { "pattern-sensitivity", P_DOUBLE, 0.0, 1.0, 0.3, {}, false }, { "left-offset", P_INT, 0, 2147483647.0, 0, {}, false },
+        { "bottom-offset", P_INT, 0, 2147483647.0, 0, {}, false } }, false, 0 },
     // smooth (gst/smooth/gstsmooth.c:40-54,76-89; instance defaults :121-126)
     { "smooth", K_SMOOTH, { "I420" }, { { "active", P_BOOL, 0, 1, 1, {}, false }, { "tolerance", P_INT, -2147483648.0, 2147483647.0, 8, {}, false },
         { "filter-size", P_INT, -2147483648.0, 2147483647.0, 3, {}, false }, { "luma-only", P_BOOL, 0, 1, 1, {}, false } }, false, 0 },
@@ -203,6 +218,12 @@ struct b200vf_element {
   int sums_cap = 0;
   b200vf_scenechange_state sc_state = { { 0, 0, 0, 0, 0 }, 0 };
   std::vector<int> last_events;            // scenechange: per frame of the last transform, 1 = force-key-unit event pushed
+  // videoanalyse: (luma-average, luma-variance); simplevideomarkdetect: (message posted, have-pattern, data) - of the
+  // last frame of the last transform call (what the shell turns into the element message)
+  std::vector<double> last_values;
+  int in_pattern = 0;                      // simplevideomarkdetect state (gstsimplevideomarkdetect.c:548)
+  uint64_t *d_u64 = nullptr;               // device scratch for sums / moments
+  int u64_cap = 0;
   // host path: per-stream staging in HBM
   cudaStream_t hs[kHostStreams] = { nullptr, nullptr, nullptr };
   uint8_t *d_in[kHostStreams] = { nullptr, nullptr, nullptr };
@@ -459,6 +480,54 @@ int run (b200vf_element *e, const uint8_t *d_in, uint8_t *d_out, int nframes, cu
       if (rc) return rc;
       return b200vf_smooth_plane (ctx, d_in + off2, s1, e->in_bytes, d_out + off2, s1, e->in_bytes, cw, ch, nframes, tol, fs, s);
     }
+    case K_VIDEOANALYSE:                                      // gst_video_analyse_transform_frame_ip, gstvideoanalyse.c:238-276
+    case K_VIDEOMARK:                                         // gst_video_mark_transform_frame_ip, gstsimplevideomark.c:465-480
+    case K_VIDEOMARKDETECT: {                                 // gst_video_detect_transform_frame_ip, gstsimplevideomarkdetect.c:567-580
+      if (d_in != d_out) B200VF_CHECK_CUDA (cudaMemcpyAsync (d_out, d_in, e->in_bytes * nframes, cudaMemcpyDeviceToDevice, s));
+      uint8_t *luma = d_out + e->yuv->luma_off;
+      const int ps = e->yuv->luma_ps;
+      b200vf_videomark_params mp = { (int) P["pattern-width"], (int) P["pattern-height"], (int) P["pattern-count"],
+        (int) P["pattern-data-count"], (int) P["left-offset"], (int) P["bottom-offset"] };
+      if (e->def->kind == K_VIDEOMARK) {
+        if (P["enabled"] == 0) return B200VF_OK;
+        return b200vf_videomark_draw (ctx, luma, ps, e->in_stride, e->in_bytes, nframes, w, h, &mp, (uint64_t) P["pattern-data"], s);
+      }
+      const int per = e->def->kind == K_VIDEOANALYSE ? 2 : B200VF_VIDEOMARK_MAX_BOXES;
+      if (e->u64_cap < per * nframes) {
+        if (e->d_u64) cudaFree (e->d_u64);
+        e->d_u64 = nullptr; e->u64_cap = 0;
+        int rc = b200vf_malloc (ctx, sizeof (uint64_t) * (size_t) per * nframes, (void **) &e->d_u64);
+        if (rc) return rc;
+        e->u64_cap = per * nframes;
+      }
+      std::vector<uint64_t> host ((size_t) per * nframes, 0);
+      int rc;
+      if (e->def->kind == K_VIDEOANALYSE) {
+        B200VF_CHECK_CUDA (cudaMemsetAsync (e->d_u64, 0, sizeof (uint64_t) * 2 * nframes, s));
+        rc = b200vf_luma_moments (ctx, luma, e->in_stride, e->in_bytes, w, h, nframes, e->d_u64, s);
+      } else {
+        rc = b200vf_videomark_box_sums (ctx, luma, ps, e->in_stride, e->in_bytes, nframes, w, h, &mp, e->d_u64, nullptr, s);
+      }
+      if (rc) return rc;
+      B200VF_CHECK_CUDA (cudaMemcpyAsync (host.data (), e->d_u64, sizeof (uint64_t) * host.size (), cudaMemcpyDeviceToHost, s));
+      B200VF_CHECK_CUDA (cudaStreamSynchronize (s));          // the element posts its message before transform_frame_ip returns
+      for (int f = 0; f < nframes; f++) {
+        if (e->def->kind == K_VIDEOANALYSE) {
+          double avg = 0, var = 0;
+          rc = b200vf_videoanalyse_finish (host[2 * f], host[2 * f + 1], w, h, &avg, &var);
+          if (rc) return rc;
+          e->last_values = { avg, var };
+        } else {
+          int message = 0;
+          uint64_t data = 0;
+          rc = b200vf_videomark_detect_decide (&mp, w, h, e->in_stride, ps, host.data () + (size_t) f * per, P["pattern-center"],
+              P["pattern-sensitivity"], &e->in_pattern, &message, &data);
+          if (rc) return rc;
+          e->last_values = { (double) message, (double) e->in_pattern, (double) data };
+        }
+      }
+      return B200VF_OK;
+    }
     case K_GEOMETRIC: {
       int rc = rebuild_index_if_needed (e, s);
       if (rc) return rc;
@@ -500,6 +569,7 @@ B200VF_API void b200vf_element_destroy (b200vf_element *e) {
   if (e->d_index) cudaFree (e->d_index);
   if (e->d_prev) cudaFree (e->d_prev);
   if (e->d_sums) cudaFree (e->d_sums);
+  if (e->d_u64) cudaFree (e->d_u64);
   delete e;
 }
 
@@ -581,7 +651,8 @@ B200VF_API int b200vf_element_set_caps (b200vf_element *e, const char *in_format
     e->in_bytes = (size_t) width * height * 4;
     e->out_stride = round_up_4 (width);
     e->out_bytes = (size_t) e->out_stride * height;
-  } else if (k == K_ZEBRASTRIPE || k == K_VIDEODIFF || k == K_SCENECHANGE || k == K_SMOOTH) {   // planar / packed YUV, same format both sides
+  } else if (k == K_ZEBRASTRIPE || k == K_VIDEODIFF || k == K_SCENECHANGE || k == K_SMOOTH || k == K_VIDEOANALYSE || k == K_VIDEOMARK ||
+      k == K_VIDEOMARKDETECT) {                                // planar / packed YUV, same format both sides
     B200VF_REQUIRE (!strcmp (in_format, out_format), B200VF_E_UNSUPPORTED, "%s: cannot convert `%s` to `%s`", e->def->name, in_format, out_format);
     B200VF_REQUIRE (in_template (in_format), B200VF_E_UNSUPPORTED, "%s: format `%s` is not in the pad template", e->def->name, in_format);
     e->yuv = find_yuv (in_format);
@@ -621,7 +692,8 @@ B200VF_API int b200vf_element_transform_device (b200vf_element *e, const void *d
   B200VF_REQUIRE (e->ctx, B200VF_E_NO_DEVICE, "%s: element has no device context (there is no CPU path)", e->def->name);
   {   // transform_frame elements get distinct buffers from the base class; only the transform_frame_ip ones may alias
     const Kind k = e->def->kind;
-    const bool ip = k == K_COLOREFFECTS || k == K_CHROMAHOLD || k == K_ZEBRASTRIPE || k == K_SCENECHANGE;
+    const bool ip = k == K_COLOREFFECTS || k == K_CHROMAHOLD || k == K_ZEBRASTRIPE || k == K_SCENECHANGE || k == K_VIDEOANALYSE ||
+        k == K_VIDEOMARK || k == K_VIDEOMARKDETECT;
     B200VF_REQUIRE (ip || d_in != d_out, B200VF_E_INVAL, "%s: transform_frame needs distinct input and output buffers", e->def->name);
   }
   return run (e, (const uint8_t *) d_in, (uint8_t *) d_out, nframes, b200vf_stream (e->ctx, stream));
@@ -670,7 +742,8 @@ B200VF_API int b200vf_element_transform (b200vf_element *e, b200vf_memory *in, b
   B200VF_REQUIRE (in->bytes >= e->in_bytes * (size_t) nframes && out->bytes >= e->out_bytes * (size_t) nframes, B200VF_E_INVAL,
       "%s: memories smaller than %d frames of the negotiated caps", e->def->name, nframes);
   const Kind k = e->def->kind;
-  const bool ip = k == K_COLOREFFECTS || k == K_CHROMAHOLD || k == K_ZEBRASTRIPE || k == K_SCENECHANGE;
+  const bool ip = k == K_COLOREFFECTS || k == K_CHROMAHOLD || k == K_ZEBRASTRIPE || k == K_SCENECHANGE || k == K_VIDEOANALYSE ||
+      k == K_VIDEOMARK || k == K_VIDEOMARKDETECT;
   B200VF_REQUIRE (ip || in != out, B200VF_E_INVAL, "%s: transform_frame needs distinct input and output buffers", e->def->name);
   cudaStream_t s = b200vf_stream (e->ctx, stream);
   std::map<std::string, double> P;
@@ -940,7 +1013,8 @@ B200VF_API int b200vf_element_transform_host (b200vf_element *e, const void *h_i
   const uint8_t *in = (const uint8_t *) h_in;
   uint8_t *out = (uint8_t *) h_out;
   // (elements that compare with the previous frame, and zebrastripe's frame counter, need the frames in order)
-  const bool ordered = e->def->kind == K_ZEBRASTRIPE || e->def->kind == K_VIDEODIFF || e->def->kind == K_SCENECHANGE;
+  const bool ordered = e->def->kind == K_ZEBRASTRIPE || e->def->kind == K_VIDEODIFF || e->def->kind == K_SCENECHANGE ||
+      e->def->kind == K_VIDEOANALYSE || e->def->kind == K_VIDEOMARKDETECT;
   std::vector<int> events;
   for (int i = 0; i < nframes; i++) {
     const int k = ordered ? 0 : i % kHostStreams;
@@ -968,6 +1042,15 @@ B200VF_API int b200vf_element_last_events (const b200vf_element *e, int *flags, 
   return n;
 }
 
+// videoanalyse: (luma-average, luma-variance); simplevideomarkdetect: (message posted, have-pattern, data) of the last frame
+// transformed - what the shells post as element messages (gstvideoanalyse.c:178-204, gstsimplevideomarkdetect.c:352-389).
+B200VF_API int b200vf_element_last_values (const b200vf_element *e, double *values, int capacity) {
+  B200VF_REQUIRE (e && (values || capacity == 0) && capacity >= 0, B200VF_E_INVAL, "last_values: bad argument");
+  const int n = (int) e->last_values.size ();
+  for (int i = 0; i < n && i < capacity; i++) values[i] = e->last_values[i];
+  return n;
+}
+
 // ------------------------------------------------------------ factory introspection
 static int fill_info (const FactoryDef &f, b200vf_factory_info *out) {
   memset (out, 0, sizeof *out);
@@ -979,7 +1062,8 @@ static int fill_info (const FactoryDef &f, b200vf_factory_info *out) {
       out->long_name = m.long_name; out->description = m.description; out->author = m.author;
     }
   B200VF_REQUIRE (out->plugin, B200VF_E_INVAL, "factory `%s` has no metadata row", f.name);
-  out->in_place = (f.kind == K_COLOREFFECTS || f.kind == K_CHROMAHOLD || f.kind == K_ZEBRASTRIPE || f.kind == K_SCENECHANGE);
+  out->in_place = (f.kind == K_COLOREFFECTS || f.kind == K_CHROMAHOLD || f.kind == K_ZEBRASTRIPE || f.kind == K_SCENECHANGE ||
+      f.kind == K_VIDEOANALYSE || f.kind == K_VIDEOMARK || f.kind == K_VIDEOMARKDETECT);
   out->n_properties = (int) f.props.size ();
   out->n_formats = (int) f.formats.size ();
   return B200VF_OK;

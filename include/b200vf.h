@@ -355,6 +355,29 @@ int b200vf_luma_moments (b200vf_ctx *ctx, const uint8_t *d_luma, int stride, siz
 int b200vf_videoanalyse_finish (uint64_t sum, uint64_t sum_sq, int width, int height, double *luma_average,
     double *luma_variance);
 
+/* simplevideomark / simplevideomarkdetect (gst/videosignal/gstsimplevideomark.c:348-462, gstsimplevideomarkdetect.c:
+ * 420-565). d_luma = the first luma sample (COMP_DATA of component 0), pixel_stride / row_stride = COMP_PSTRIDE /
+ * COMP_STRIDE. The boxes - pattern-count calibration boxes alternating black / white, then pattern-data-count boxes
+ * spelling pattern-data (most significant bit first) - are walked on the host exactly as the reference walks them
+ * (clipping, early exits); at most B200VF_VIDEOMARK_MAX_BOXES are supported.
+ *   b200vf_videomark_draw: the mark, in place, one launch per batch.
+ *   b200vf_videomark_box_sums: d_sums[f * B200VF_VIDEOMARK_MAX_BOXES + k] = sum of the samples of box k of frame f
+ *     (the detector averages the FULL pattern width even where a box is clipped, as the reference does); *n_boxes = how
+ *     many boxes the walk visits. Device result: copy it out after the stream has run.
+ *   b200vf_videomark_detect_decide (host): the reference's decisions on one frame's sums; *in_pattern is the element's
+ *     state, *message = 1 when the element would post its message (have-pattern = *in_pattern afterwards, data = *data). */
+#define B200VF_VIDEOMARK_MAX_BOXES 128
+typedef struct b200vf_videomark_params {
+  int pattern_width, pattern_height, pattern_count, pattern_data_count, left_offset, bottom_offset;
+} b200vf_videomark_params;
+int b200vf_videomark_draw (b200vf_ctx *ctx, uint8_t *d_luma, int pixel_stride, int row_stride, size_t frame_stride,
+    int nframes, int width, int height, const b200vf_videomark_params *params, uint64_t pattern_data, void *stream);
+int b200vf_videomark_box_sums (b200vf_ctx *ctx, const uint8_t *d_luma, int pixel_stride, int row_stride, size_t frame_stride,
+    int nframes, int width, int height, const b200vf_videomark_params *params, uint64_t *d_sums, int *n_boxes, void *stream);
+int b200vf_videomark_detect_decide (const b200vf_videomark_params *params, int width, int height, int row_stride,
+    int pixel_stride, const uint64_t *sums, double pattern_center, double pattern_sensitivity, int *in_pattern, int *message,
+    uint64_t *data);
+
 /* ------------------------------------------------------------ smooth plugin
  * smooth_filter (gst/smooth/gstsmooth.c:131-176) on one 8-bit plane: the mean
  * (integer division) of the reference sample and of the window samples within
@@ -480,6 +503,10 @@ int b200vf_element_transform (b200vf_element *e, b200vf_memory *in, b200vf_memor
  * scene change, i.e. where the reference pushes its downstream force-key-unit
  * event (gstscenechange.c:246-257). Returns the number of frames of that call. */
 int b200vf_element_last_events (const b200vf_element *e, int *flags, int capacity);
+/* videoanalyse: values = (luma-average, luma-variance); simplevideomarkdetect: (message posted 0/1, have-pattern 0/1,
+ * data) - of the last frame transformed: the fields of the element messages the reference posts
+ * (gstvideoanalyse.c:178-204, gstsimplevideomarkdetect.c:352-389). Returns how many values there are. */
+int b200vf_element_last_values (const b200vf_element *e, double *values, int capacity);
 
 /* ------------------------------------------------- factory introspection
  * What gst-inspect prints for each element, so that the C/GLib shells (gst/gstb200vf.c) can register the
@@ -501,7 +528,8 @@ typedef struct b200vf_factory_info {
   int n_properties;
   int n_formats;                  /* raw video formats of the pad template (sink == src except the bayer elements) */
 } b200vf_factory_info;
-typedef enum b200vf_prop_type { B200VF_PROP_UINT = 0, B200VF_PROP_INT, B200VF_PROP_BOOL, B200VF_PROP_DOUBLE, B200VF_PROP_ENUM } b200vf_prop_type;
+typedef enum b200vf_prop_type { B200VF_PROP_UINT = 0, B200VF_PROP_INT, B200VF_PROP_BOOL, B200VF_PROP_DOUBLE, B200VF_PROP_ENUM,
+  B200VF_PROP_UINT64 /* carried as a double: exact up to 2^53 */ } b200vf_prop_type;
 typedef struct b200vf_property_info {
   const char *name;
   int type;                       /* b200vf_prop_type */

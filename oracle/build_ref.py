@@ -482,6 +482,63 @@ void ref_videoanalyse (guint8 *luma, int stride, int width, int height, double *
 }
 """)
 
+# ------------------------------------------------------------- videosignal: simplevideomark / simplevideomarkdetect
+VM_FRAME_SHIM = """
+typedef int GstFlowReturn;
+#define GST_FLOW_OK 0
+typedef struct { struct { int width, height; } info; guint8 *data0; int stride0, pstride0; void *buffer; } GstVideoFrame;
+#define GST_VIDEO_FRAME_COMP_STRIDE(f,c) ((f)->stride0)
+#define GST_VIDEO_FRAME_COMP_PSTRIDE(f,c) ((f)->pstride0)
+#define GST_VIDEO_FRAME_COMP_DATA(f,c) ((f)->data0)
+#define GST_ERROR_OBJECT(...) do { } while (0)
+#define G_GUINT64_CONSTANT(v) (v##ULL)
+#define G_GUINT64_FORMAT "lu"
+typedef void GstBuffer;
+"""
+TUS["ref_videomark.c"] = lambda: (
+    "#include <glib.h>\n" + VM_FRAME_SHIM
+    + "typedef struct { gint pattern_width, pattern_height, pattern_count, pattern_data_count; guint64 pattern_data;\n"
+      "  gboolean enabled; gint left_offset, bottom_offset; } GstSimpleVideoMark;\n"
+    + func("gst/videosignal/gstsimplevideomark.c", "gst_video_mark_draw_box")
+    + func("gst/videosignal/gstsimplevideomark.c", "calculate_pw")
+    + func("gst/videosignal/gstsimplevideomark.c", "gst_video_mark_yuv")
+    + """
+void ref_videomark (guint8 *data, int stride, int pstride, int width, int height, int pw, int ph, int pc, int pdc,
+    guint64 pdata, int left, int bottom)
+{
+  GstSimpleVideoMark m = { pw, ph, pc, pdc, pdata, TRUE, left, bottom };
+  GstVideoFrame f;
+  f.info.width = width; f.info.height = height; f.data0 = data; f.stride0 = stride; f.pstride0 = pstride; f.buffer = 0;
+  gst_video_mark_yuv (&m, &f);
+}
+""")
+
+TUS["ref_videomarkdetect.c"] = lambda: (
+    "#include <glib.h>\n" + VM_FRAME_SHIM
+    + "typedef struct { gboolean message; gint pattern_width, pattern_height, pattern_count, pattern_data_count;\n"
+      "  gdouble pattern_center, pattern_sensitivity; gint left_offset, bottom_offset; gboolean in_pattern; } GstSimpleVideoMarkDetect;\n"
+      "static int ref_msgs; static guint64 ref_last_data;\n"
+      "static void gst_video_detect_post_message (GstSimpleVideoMarkDetect *d, GstBuffer *b, guint64 data) { ref_msgs++; ref_last_data = data; }\n"
+    + func("gst/videosignal/gstsimplevideomarkdetect.c", "gst_video_detect_calc_brightness")
+    + func("gst/videosignal/gstsimplevideomarkdetect.c", "calculate_pw")
+    + func("gst/videosignal/gstsimplevideomarkdetect.c", "gst_video_detect_yuv")
+    + """
+/* one frame; *in_pattern is the element's state across frames; returns the number of messages posted (0 or 1) and,
+ * when one was, its "data" field */
+int ref_videomarkdetect (guint8 *data, int stride, int pstride, int width, int height, int pw, int ph, int pc, int pdc,
+    double center, double sensitivity, int left, int bottom, int *in_pattern, guint64 *msg_data)
+{
+  GstSimpleVideoMarkDetect d = { TRUE, pw, ph, pc, pdc, center, sensitivity, left, bottom, *in_pattern };
+  GstVideoFrame f;
+  f.info.width = width; f.info.height = height; f.data0 = data; f.stride0 = stride; f.pstride0 = pstride; f.buffer = 0;
+  ref_msgs = 0; ref_last_data = 0;
+  gst_video_detect_yuv (&d, &f);
+  *in_pattern = d.in_pattern;
+  *msg_data = ref_last_data;
+  return ref_msgs;
+}
+""")
+
 TUS["ref_smooth.c"] = lambda: (
     "#include <glib.h>\n"
     + func("gst/smooth/gstsmooth.c", "smooth_filter")

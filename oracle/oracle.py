@@ -225,6 +225,115 @@ class Port(_Base):
         self.lib.oracle_videoanalyse(_p(luma), luma.shape[1], width, height, C.byref(a), C.byref(v))
         return a.value, v.value
 
+    # simplevideomark / simplevideomarkdetect: a pure-Python restatement (a few hundred samples per frame) of
+    # gst_video_mark_yuv (gst/videosignal/gstsimplevideomark.c:348-462) and gst_video_detect_yuv
+    # (gstsimplevideomarkdetect.c:420-565): the same walk over the boxes, statement for statement.
+    @staticmethod
+    def _calculate_pw(pw, x, width):                          # :336-345
+        if x < 0:
+            return pw + x
+        if x + pw > width:
+            return width - x
+        return pw
+
+    def videomark(self, frame, pixel_stride, width, height, pw=4, ph=16, pc=4, pdc=5, data=10, left=0, bottom=0):
+        out = np.ascontiguousarray(frame, np.uint8).copy()
+        flat = out.reshape(-1)
+        rs = out.shape[1]
+        offset = rs * (height - ph - bottom) + pixel_stride * left
+        x, y, total = left, height - ph - bottom, pc + pdc
+        if (x + pw * total) < 0 or x > width or (y + height) < 0 or y > height:
+            return out
+        offset = max(offset, 0)
+        if y < 0:
+            ph += y
+        elif y + ph > height:
+            ph = height - y
+        if ph < 0:
+            return out
+        d = offset
+
+        def box(d, w, color):
+            for i in range(ph):
+                for j in range(w):
+                    flat[d + i * rs + pixel_stride * j] = color
+        for i in range(pc):
+            dpw = self._calculate_pw(pw, x, width)
+            if dpw < 0:
+                continue
+            box(d, dpw, 255 if i & 1 else 0)
+            d += pixel_stride * dpw
+            x += dpw
+            if (x + pw * (total - i - 1)) < 0 or x >= width:
+                return out
+        shift = 1 << (pdc - 1) if pdc > 0 else 0
+        for i in range(pdc):
+            dpw = self._calculate_pw(pw, x, width)
+            if dpw < 0:
+                continue
+            box(d, dpw, 255 if data & shift else 0)
+            shift >>= 1
+            d += pixel_stride * dpw
+            x += dpw
+            if (x + pw * (pdc - i - 1)) < 0 or x >= width:
+                return out
+        return out
+
+    def videomarkdetect(self, frame, pixel_stride, width, height, pw=4, ph=16, pc=4, pdc=5, center=0.5, sensitivity=0.3, left=0,
+                        bottom=0, in_pattern=False):
+        f = np.ascontiguousarray(frame, np.uint8)
+        flat = f.reshape(-1)
+        rs = f.shape[1]
+        offset = rs * (height - ph - bottom) + pixel_stride * left
+        x, y, total = left, height - ph - bottom, pc + pdc
+        if (x + pw * total) < 0 or x > width or (y + height) < 0 or y > height:
+            return in_pattern, False, 0
+        offset = max(offset, 0)
+        if y < 0:
+            ph += y
+        elif y + ph > height:
+            ph = height - y
+        if ph < 0:
+            return in_pattern, False, 0
+        d = offset
+
+        def brightness(d):                                    # :392-407; samples past the plane count as 0 here (undefined there)
+            s = 0
+            for i in range(ph):
+                for j in range(pw):
+                    o = d + i * rs + pixel_stride * j
+                    s += int(flat[o]) if o < flat.size else 0
+            den = 255.0 * pw * ph
+            return s / den if den else float("nan")
+        for i in range(pc):
+            b = brightness(d)
+            if i & 1:
+                if b < center + sensitivity:
+                    return False, bool(in_pattern), 0
+            elif b > center - sensitivity:
+                return False, bool(in_pattern), 0
+            dpw = self._calculate_pw(pw, x, width)
+            if dpw < 0:
+                continue
+            d += pixel_stride * dpw
+            x += dpw
+            if (x + pw * (total - i - 1)) < 0 or x >= width:
+                break
+        data = 0
+        for i in range(pdc):
+            b = brightness(d)
+            data <<= 1
+            if b > center:
+                data |= 1
+            dpw = self._calculate_pw(pw, x, width)
+            if dpw < 0:
+                continue
+            d += pixel_stride * dpw
+            x += dpw
+            if (x + pw * (pdc - i - 1)) < 0 or x >= width:
+                break
+        return True, True, data
+
     def smooth_plane(self, plane, width, height, tolerance=8, filtersize=3, prefill=0):
         """returns the filtered plane; rows the reference never writes keep `prefill`"""
         plane = _u8(plane)
@@ -410,6 +519,22 @@ class Ref(_Base):
         self.lib.ref_scenechange_score.restype = C.c_double
         self.lib.ref_scenechange_score(_p(a), a.shape[1], _p(b), b.shape[1], width, height, C.byref(sad))
         return int(sad.value)
+
+    def videomark(self, frame, pixel_stride, width, height, pw=4, ph=16, pc=4, pdc=5, data=10, left=0, bottom=0):
+        """gst_video_mark_yuv on a copy of `frame` (rows of the plane; luma at byte 0 of every pixel_stride bytes)"""
+        out = np.ascontiguousarray(frame, np.uint8).copy()
+        self.lib.ref_videomark(_p(out), out.shape[1], pixel_stride, width, height, pw, ph, pc, pdc, C.c_uint64(data), left, bottom)
+        return out
+
+    def videomarkdetect(self, frame, pixel_stride, width, height, pw=4, ph=16, pc=4, pdc=5, center=0.5, sensitivity=0.3, left=0,
+                        bottom=0, in_pattern=False):
+        """gst_video_detect_yuv on one frame -> (in_pattern, message posted, data)"""
+        f = np.ascontiguousarray(frame, np.uint8)
+        ip, data = C.c_int(int(in_pattern)), C.c_uint64(0)
+        self.lib.ref_videomarkdetect.restype = C.c_int
+        n = self.lib.ref_videomarkdetect(_p(f), f.shape[1], pixel_stride, width, height, pw, ph, pc, pdc, C.c_double(center),
+                                         C.c_double(sensitivity), left, bottom, C.byref(ip), C.byref(data))
+        return bool(ip.value), bool(n), int(data.value)
 
     def videoanalyse(self, luma, width, height):
         luma = _u8(luma)

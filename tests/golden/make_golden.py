@@ -68,7 +68,7 @@ def make_surface():
     """element_surface.json from the reference's own API dump"""
     cache = json.load(open(os.path.join(REF, "docs", "plugins", "gst_plugins_cache.json")))
     want = {"bayer": ["bayer2rgb", "rgb2bayer"], "gaudieffects": None, "coloreffects": None, "geometrictransform": None,
-            "videofiltersbad": ["zebrastripe", "videodiff", "scenechange"], "smooth": None}
+            "videofiltersbad": ["zebrastripe", "videodiff", "scenechange"], "smooth": None, "videosignal": None}
     surf = {}
     for plugin, only in want.items():
         for name, el in cache[plugin]["elements"].items():

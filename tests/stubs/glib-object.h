@@ -37,6 +37,7 @@ typedef enum { G_TYPE_FLAG_NONE = 0, G_TYPE_FLAG_ABSTRACT = 1 << 4 } GTypeFlags;
 #define G_TYPE_BOOLEAN G_TYPE_MAKE_FUNDAMENTAL (5)
 #define G_TYPE_INT G_TYPE_MAKE_FUNDAMENTAL (6)
 #define G_TYPE_UINT G_TYPE_MAKE_FUNDAMENTAL (7)
+#define G_TYPE_UINT64 G_TYPE_MAKE_FUNDAMENTAL (11)
 #define G_TYPE_ENUM G_TYPE_MAKE_FUNDAMENTAL (12)
 #define G_TYPE_DOUBLE G_TYPE_MAKE_FUNDAMENTAL (15)
 #define G_TYPE_OBJECT G_TYPE_MAKE_FUNDAMENTAL (20)
@@ -45,6 +46,7 @@ gboolean g_type_check_value_holds (const GValue * value, GType type);
 #define G_VALUE_HOLDS_BOOLEAN(value) (G_VALUE_HOLDS ((value), G_TYPE_BOOLEAN))
 #define G_VALUE_HOLDS_INT(value) (G_VALUE_HOLDS ((value), G_TYPE_INT))
 #define G_VALUE_HOLDS_UINT(value) (G_VALUE_HOLDS ((value), G_TYPE_UINT))
+#define G_VALUE_HOLDS_UINT64(value) (G_VALUE_HOLDS ((value), G_TYPE_UINT64))
 #define G_VALUE_HOLDS_DOUBLE(value) (G_VALUE_HOLDS ((value), G_TYPE_DOUBLE))
 #define G_VALUE_HOLDS_ENUM(value) (G_VALUE_HOLDS ((value), G_TYPE_ENUM))
 #define G_OBJECT_CLASS(klass) ((GObjectClass *) (klass))
@@ -53,6 +55,8 @@ gboolean g_type_check_value_holds (const GValue * value, GType type);
 GValue *g_value_init (GValue * value, GType g_type);
 void g_value_unset (GValue * value);
 guint g_value_get_uint (const GValue * value);
+guint64 g_value_get_uint64 (const GValue * value);
+void g_value_set_uint64 (GValue * value, guint64 v);
 gint g_value_get_int (const GValue * value);
 gboolean g_value_get_boolean (const GValue * value);
 gdouble g_value_get_double (const GValue * value);
@@ -68,6 +72,7 @@ GValueArray *g_value_array_new (guint n_prealloced);
 GValueArray *g_value_array_append (GValueArray * value_array, const GValue * value);
 GValue *g_value_array_get_nth (GValueArray * value_array, guint index_);
 GParamSpec *g_param_spec_uint (const gchar * name, const gchar * nick, const gchar * blurb, guint minimum, guint maximum, guint default_value, GParamFlags flags);
+GParamSpec *g_param_spec_uint64 (const gchar * name, const gchar * nick, const gchar * blurb, guint64 minimum, guint64 maximum, guint64 default_value, GParamFlags flags);
 GParamSpec *g_param_spec_int (const gchar * name, const gchar * nick, const gchar * blurb, gint minimum, gint maximum, gint default_value, GParamFlags flags);
 GParamSpec *g_param_spec_boolean (const gchar * name, const gchar * nick, const gchar * blurb, gboolean default_value, GParamFlags flags);
 GParamSpec *g_param_spec_double (const gchar * name, const gchar * nick, const gchar * blurb, gdouble minimum, gdouble maximum, gdouble default_value, GParamFlags flags);

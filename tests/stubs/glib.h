@@ -27,6 +27,7 @@ typedef unsigned long gulong;
 #define G_BEGIN_DECLS
 #define G_END_DECLS
 #define G_MAXDOUBLE 1.7976931348623157e308
+#define G_MAXUINT64 0xffffffffffffffffULL
 #define G_GSIZE_FORMAT "lu"
 #define MAX(a, b) (((a) > (b)) ? (a) : (b))
 #define MIN(a, b) (((a) < (b)) ? (a) : (b))

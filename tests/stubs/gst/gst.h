@@ -104,6 +104,7 @@ typedef struct _GstBufferPoolClass GstBufferPoolClass;
 typedef struct _GstBuffer { GstMiniObject mini_object; GstBufferPool *pool; GstClockTime pts; GstClockTime dts; GstClockTime duration; guint64 offset; guint64 offset_end; } GstBuffer;
 #define GST_BUFFER_PTS(buf) (((GstBuffer *) (buf))->pts)
 #define GST_BUFFER_TIMESTAMP(buf) GST_BUFFER_PTS (buf)
+#define GST_BUFFER_DURATION(buf) (((GstBuffer *) (buf))->duration)
 GstBuffer *gst_buffer_new (void);
 void gst_buffer_append_memory (GstBuffer * buffer, GstMemory * mem);
 guint gst_buffer_n_memory (GstBuffer * buffer);
@@ -158,12 +159,19 @@ typedef enum { GST_RANK_NONE = 0 } GstRank;
 typedef enum { GST_FORMAT_UNDEFINED = 0, GST_FORMAT_TIME = 3 } GstFormat;
 typedef struct _GstSegment { guint flags; gdouble rate; gdouble applied_rate; GstFormat format; guint64 base, offset, start, stop, time, position, duration; } GstSegment;
 guint64 gst_segment_to_stream_time (const GstSegment * segment, GstFormat format, guint64 position);
+guint64 gst_segment_to_running_time (const GstSegment * segment, GstFormat format, guint64 position);
 GstPadTemplate *gst_pad_template_new (const gchar * name_template, GstPadDirection direction, GstPadPresence presence, GstCaps * caps);
 void gst_element_class_add_pad_template (GstElementClass * klass, GstPadTemplate * templ);
 void gst_element_class_set_static_metadata (GstElementClass * klass, const gchar * longname, const gchar * classification,
     const gchar * description, const gchar * author);
 gboolean gst_element_register (GstPlugin * plugin, const gchar * name, guint rank, GType type);
 gboolean gst_pad_push_event (GstPad * pad, GstEvent * event);
+typedef struct _GstMessage GstMessage;
+GstStructure *gst_structure_new (const gchar * name, const gchar * firstfield, ...);
+GstMessage *gst_message_new_element (GstObject * src, GstStructure * structure);
+gboolean gst_element_post_message (GstElement * element, GstMessage * message);
+#define GST_ELEMENT_CAST(obj) ((GstElement *) (obj))
+#define GST_OBJECT_CAST(obj) ((GstObject *) (obj))
 typedef gboolean (*GstPluginInitFunc) (GstPlugin * plugin);
 typedef struct _GstPluginDesc {
   gint major_version, minor_version; const gchar *name, *description; GstPluginInitFunc plugin_init;

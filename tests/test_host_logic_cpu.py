@@ -246,14 +246,15 @@ def test_factory_introspection_matches_reference_api_dump(vf):
         assert f["plugin"] == e["plugin"] and f["type_name"] == e["hierarchy"][0] and f["parent_type_name"] == e["hierarchy"][1]
         assert f["klass"] == e["klass"] and f["long_name"] == e["long-name"] and f["description"] == e["description"]
         assert f["author"] == e["author"] and f["plugin_license"] == e["plugin-license"]
-        assert f["in_place"] == (1 if name in ("coloreffects", "chromahold", "zebrastripe", "scenechange") else 0)   # transform_frame_ip
+        assert f["in_place"] == (1 if name in ("coloreffects", "chromahold", "zebrastripe", "scenechange", "videoanalyse", "simplevideomark",
+                                               "simplevideomarkdetect") else 0)   # transform_frame_ip
         props = {p["name"]: p for p in f["properties"]}
         for pn, pd in e["properties"].items():
             if pd["type"] == "GValueArray":
                 assert all(not props["matrix-%d" % i]["controllable"] for i in range(9))
                 continue
             assert props[pn]["controllable"] == bool(pd.get("controllable")), (name, pn)
-            kind = {"guint": 0, "gint": 1, "gboolean": 2, "gdouble": 3}.get(pd["type"], 4)
+            kind = {"guint": 0, "gint": 1, "gboolean": 2, "gdouble": 3, "guint64": 5}.get(pd["type"], 4)
             assert props[pn]["type"] == kind, (name, pn, pd["type"])
         caps = e["pad-templates"]["src" if name == "rgb2bayer" else "sink"] if name not in ("bayer2rgb",) else e["pad-templates"]["src"]
         if name == "rgb2bayer":

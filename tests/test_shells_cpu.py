@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GST = os.path.join(ROOT, "gst-plugins-bad_b200", "gst")
 FLAGS = ["gcc", "-std=gnu11", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused-function",
          "-I" + os.path.join(ROOT, "tests", "stubs"), "-I" + os.path.join(ROOT, "include"), "-I" + GST]
-PLUGINS = ["bayer", "gaudieffects", "coloreffects", "geometrictransform", "videofiltersbad", "smooth"]
+PLUGINS = ["bayer", "gaudieffects", "coloreffects", "geometrictransform", "videofiltersbad", "smooth", "videosignal"]
 
 
 @pytest.mark.parametrize("plugin", PLUGINS)

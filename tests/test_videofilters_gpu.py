@@ -281,3 +281,94 @@ def test_videoanalyse_8k_needs_64_bit_sums(ctx, vf):
     got = ctx.download(d_sums, 16).view(np.uint64)
     assert (int(got[0]), int(got[1])) == (255 * w * h, 255 * 255 * w * h)      # 8.5e9 and 2.2e12
     assert vf.videoanalyse_finish(int(got[0]), int(got[1]), w, h) == (1.0, 0.0)
+
+
+# ---------------------------------------------------------------- videosignal: simplevideomark / simplevideomarkdetect
+def _mark_cases(rng, n):
+    for _ in range(n):
+        w, h = int(rng.integers(8, 200)), int(rng.integers(4, 90))
+        ps = int(rng.choice([1, 2, 4]))
+        st = frames.round_up_4(w * ps + int(rng.integers(0, 3)) * 4)
+        kw = dict(pw=int(rng.integers(1, 12)), ph=int(rng.integers(1, h + 8)), pc=int(rng.integers(0, 7)), pdc=int(rng.integers(0, 12)),
+                  left=int(rng.integers(0, w + 4)), bottom=int(rng.integers(0, h + 3)))
+        yield w, h, ps, st, kw, int(rng.integers(0, 1 << 12))
+
+
+def test_simplevideomark_draws_the_references_boxes(ctx, vf, orc, rng):
+    """gst_video_mark_yuv (gstsimplevideomark.c:348-462): boxes clipped at the right / top edge, offsets beyond the
+    frame (nothing drawn), zero counts, packed layouts (pixel stride 2 and 4) - 120 random configurations + defaults"""
+    cases = list(_mark_cases(rng, 120)) + [(640, 480, 1, 640, dict(pw=4, ph=16, pc=4, pdc=5, left=0, bottom=0), 10)]
+    for (w, h, ps, st, kw, data) in cases:
+        fr = rng.integers(0, 256, (h, st), dtype=np.uint8)
+        p = vf.VideoMarkParams(kw["pw"], kw["ph"], kw["pc"], kw["pdc"], kw["left"], kw["bottom"])
+        d = up(ctx, fr)
+        ctx.videomark_draw(d, ps, st, w, h, p, pattern_data=data)
+        got = ctx.download(d, h * st).reshape(h, st)
+        want = orc.videomark(fr, ps, w, h, data=data, **kw)
+        assert np.array_equal(got, want), (w, h, ps, kw, np.argwhere(got != want)[:4])
+
+
+def test_simplevideomarkdetect_reads_what_simplevideomark_wrote(ctx, vf, orc, rng):
+    """box sums on the GPU + the reference's decisions on the host == gst_video_detect_yuv, on marked and unmarked frames,
+    from both states of in_pattern (a pattern that disappears posts have-pattern = false once)"""
+    for (w, h, ps, st, kw, data) in list(_mark_cases(rng, 80)) + [(640, 480, 1, 640, dict(pw=4, ph=16, pc=4, pdc=5, left=0, bottom=0), 21)]:
+        # two rows of slack: where a clipped box is averaged over its FULL width the reference reads on into the next rows
+        fr = np.zeros((h + 2, st), np.uint8)
+        fr[:h] = rng.integers(0, 256, (h, st), dtype=np.uint8)
+        marked = orc.videomark(fr, ps, w, h, data=data, **kw)
+        p = vf.VideoMarkParams(kw["pw"], kw["ph"], kw["pc"], kw["pdc"], kw["left"], kw["bottom"])
+        for frame in (fr, marked):
+            sums = ctx.videomark_box_sums(up(ctx, frame[:h]), ps, st, w, h, p)[0]
+            for ip in (False, True):
+                got = vf.videomark_detect_decide(p, w, h, st, ps, sums, 0.5, 0.3, ip)
+                want = orc.videomarkdetect(frame, ps, w, h, in_pattern=ip, **{k: v for k, v in kw.items()})
+                # (the plane handed to the GPU ends at row h: samples the reference reads in the slack rows are zero on both sides)
+                assert got == want, (w, h, ps, kw, ip, got, want)
+    # the default mark on a default-sized frame carries its data
+    fr = np.full((480, 640), 128, np.uint8)
+    marked = orc.videomark(fr, 1, 640, 480, data=21)
+    p = vf.VideoMarkParams()
+    assert vf.videomark_detect_decide(p, 640, 480, 640, 1, ctx.videomark_box_sums(up(ctx, marked), 1, 640, 640, 480, p)[0]) == (True, True, 21)
+
+
+def test_videosignal_elements(ctx, vf, orc, rng):
+    """simplevideomark ! simplevideomarkdetect and videoanalyse through the element mirror (I420 and UYVY), on memories:
+    the frame stays in HBM, the detector / analyser bring back a few numbers"""
+    w, h = 320, 240
+    for fmt, ps, off in (("I420", 1, 0), ("UYVY", 2, 1)):
+        mark, det = ctx.element("simplevideomark"), ctx.element("simplevideomarkdetect")
+        for e in (mark, det):
+            e.set_caps(fmt, fmt, w, h)
+            e.set_property("pattern-width", 6)
+            e.set_property("left-offset", 10)
+        mark.set_property("pattern-data", 19)
+        n_in, _ = mark.unit_size()
+        fr = rng.integers(0, 256, n_in, dtype=np.uint8)
+        m = ctx.memory(n_in)
+        m.write(fr)
+        c0 = ctx.transfer_counts()
+        mark.transform_mem(m, m)
+        det.transform_mem(m, m)
+        assert det.last_values() == [1.0, 1.0, 19.0]
+        c1 = ctx.transfer_counts()
+        assert (c1[0] - c0[0], c1[2] - c0[2]) == (1, 0)         # one upload, nothing downloaded through the memory
+        got = m.read()
+        st = frames.round_up_4(w * ps)
+        plane = fr[: st * h].reshape(h, st).copy()
+        want = orc.videomark(plane[:, off:] if off else plane, ps, w, h, pw=6, left=10, data=19) if not off else None
+        if not off:
+            assert np.array_equal(got[: st * h].reshape(h, st), want) and np.array_equal(got[st * h:], fr[st * h:])
+        mark.set_property("enabled", False)
+        m.write(fr)
+        mark.transform_mem(m, m)
+        det.transform_mem(m, m)
+        assert det.last_values()[:2] == [1.0, 0.0]                  # the pattern disappeared: one message, have-pattern false
+        det.transform_mem(m, m)
+        assert det.last_values()[0] == 0.0                          # ... and none after that
+    va = ctx.element("videoanalyse")
+    va.set_caps("I420", "I420", w, h)
+    fr = rng.integers(0, 256, va.unit_size()[0], dtype=np.uint8)
+    out = va.transform(fr)
+    assert np.array_equal(out, fr)
+    avg, var = orc.videoanalyse(fr[: w * h].reshape(h, w), w, h)
+    assert va.last_values() == [avg, var]
