@@ -1,5 +1,5 @@
 """Runs one element kernel a few times (for ncu -k regex:... captures of kernels bench.py --profile does not reach).
-   python tools/run_one.py gaussblur|dilate|exclusion|chromahold|remap|remap_packed|lut4|direct|rgb2bayer|sad|videodiff|zebrastripe|smooth [4k|8k]"""
+   python tools/run_one.py gaussblur|dilate|exclusion|chromahold|remap|remap_packed|lut4|coloreffects|fused|moments|direct|rgb2bayer|sad|videodiff|zebrastripe|smooth [4k|8k]"""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gst-plugins-bad_b200"))
@@ -35,6 +35,17 @@ elif what in ("sad", "videodiff", "zebrastripe", "smooth"):        # videofilter
          "videodiff": lambda: ctx.videodiff_luma(la, lb, lo, w, w, h, nframes=nl, stream=st),
          "zebrastripe": lambda: ctx.zebrastripe(lb, 1, w, w, h, threshold=90, nframes=nl, stream=st),
          "smooth": lambda: ctx.smooth_plane(la, lo, w, w, h, nframes=2, stream=st)}[what]
+elif what == "coloreffects":
+    table, ml = b200vf.coloreffects_table(2)
+    f = lambda: ctx.coloreffects_rgb(a, w, h, 4 * w, 4, (0, 1, 2), table, ml, nframes=n, stream=st)
+elif what == "fused":
+    src = torch.randint(0, 255, (8, h, w), dtype=torch.uint8, device="cuda"); dst = torch.empty((8, h, 4 * w), dtype=torch.uint8, device="cuda")
+    table, ml = b200vf.coloreffects_table(2); sol = b200vf.lut_solarize()
+    f = lambda: ctx.bayer2rgb_fused(src, w, dst, 4 * w, w, h, 0, (0, 1, 2), luma_table=table, lut=sol, nframes=8, stream=st)
+elif what == "moments":
+    nl = 32 if size == "4k" else 8
+    la = torch.randint(0, 255, (nl, h, w), dtype=torch.uint8, device="cuda"); mom = torch.zeros(2 * nl, dtype=torch.int64, device="cuda")
+    f = lambda: ctx.luma_moments(la, w, w, h, mom, nframes=nl, stream=st)
 elif what == "rgb2bayer":
     mosaic = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
     f = lambda: ctx.rgb2bayer(a, 4 * w, mosaic, w, w, h, 0, nframes=n, stream=st)
