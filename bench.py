@@ -586,7 +586,7 @@ def summary(line):
         "C3_gaussblur_sigma5_4k_ayuv": g("gaussblur_sigma5_4k_exact", "fps", "frac_fp32", "kernel"),
         "C3_gaussblur_sigma5_4k_bgrx": g("gaussblur_sigma5_4k_exact_bgrx", "fps", "frac_fp32"),
         "C3_gaussblur_sigma5_8k_ayuv": g("gaussblur_sigma5_8k_exact", "fps", "frac_fp32"),
-        "C4_fisheye_8k": g("fisheye_8k_remap", "fps", "frac_hbm"),
+        "C4_fisheye_8k": g("fisheye_8k_remap", "fps", "frac_hbm", "host_map_build_s", "device_table_build_s", "device_table_equals_host"),
         "C4_fisheye_8k_single_frame": g("fisheye_8k_remap_single_frame", "fps", "frac_hbm", "frac_hbm_with_index"),
         "C5_chain_8k_fused": g("chain_8k_fused", "fps", "frac_hbm"),
         "C5_chain_8k_unfused": g("chain_8k_unfused", "fps"),
@@ -711,8 +711,18 @@ def side_measurements(ctx, torch, b200vf, st, side, peak):
             idx = b200vf.gt_resolve_map(m, w, h, 1)
             t_map = time.perf_counter() - t0
             d_idx = torch.from_numpy(idx).cuda()
+            # the same table built on the GPU (certified against glibc, uncertain entries patched in from the host)
+            b200vf.gt_build_index_device(ctx, "fisheye", w, h, {}, 1).free()
+            t0 = time.perf_counter()
+            d_dev = b200vf.gt_build_index_device(ctx, "fisheye", w, h, {}, 1)
+            t_dev = time.perf_counter() - t0
+            dev_equal = bool(torch.equal(torch.from_numpy(ctx.download(d_dev, w * h * 4, dtype=np.int32)), torch.from_numpy(idx.reshape(-1))))
+            d_dev.free()
             t = timeit(lambda: ctx.remap(a, b, d_idx, w, h, 4, 4 * w, nframes=n4, stream=st))
-            rec("fisheye_8k_remap", n4, px, 8, t, {"host_map_build_s": t_map, "index_table_bytes_per_px": 4,
+            rec("fisheye_8k_remap", n4, px, 8, t, {"host_map_build_s": t_map, "device_table_build_s": t_dev,
+                                                   "device_table_equals_host": dev_equal,
+                                                   "device_table_entries_from_host": b200vf.gt_device_last_uncertain(),
+                                                   "index_table_bytes_per_px": 4,
                                                    "note": "batch of %d frames per launch: the 4 B/px index is shared through L2" % n4})
             # one frame per launch over a ring of frames larger than L2: the index table (132.7 MB, larger than L2 itself)
             # comes from HBM for every frame: 8 B/px credited, 12 B/px moved

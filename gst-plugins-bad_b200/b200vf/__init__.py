@@ -100,6 +100,7 @@ _SIGS = {
     "b200vf_chromahold": (_i, [_vp, _vp, _i, _i, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200vf_gt_build_map": (_i, [C.c_char_p, _i, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_double), _i, _vp]),
     "b200vf_gt_device_map_supported": (_i, [C.c_char_p]),
+    "b200vf_gt_device_last_uncertain": (C.c_longlong, []),
     "b200vf_gt_build_index_device": (_i, [_vp, C.c_char_p, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "b200vf_gt_resolve_map": (_i, [_vp, _i, _i, _i, _vp]),
     "b200vf_remap": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _sz, _i, _u32, _vp]),
@@ -603,11 +604,18 @@ def gt_build_map(element, width, height, props=None):
 
 
 def gt_device_map_supported(element):
-    return bool(lib.b200vf_gt_device_map_supported(element.encode()))
+    """0: no device map; 1: evaluated exactly on the GPU; 2: certified on the GPU, uncertain entries patched in from the host"""
+    return lib.b200vf_gt_device_map_supported(element.encode())
+
+
+def gt_device_last_uncertain():
+    """entries the last gt_build_index_device on this thread took from the host's map function"""
+    return lib.b200vf_gt_device_last_uncertain()
 
 
 def gt_build_index_device(ctx, element, width, height, props=None, off_edge=0, stream=None):
-    """the int32 gather table built on the GPU (mirror, square, stretch, bulge, tunnel, perspective); returns a DeviceBuffer"""
+    """the int32 gather table built on the GPU (every map but `diffuse`); returns a DeviceBuffer. E_UNSUPPORTED when a
+    libm map cannot be certified (too many coordinates on integers): build on the host then"""
     props = props or {}
     names = (C.c_char_p * max(1, len(props)))(*[k.replace("_", "-").encode() for k in props])
     vals = (C.c_double * max(1, len(props)))(*[float(v) for v in props.values()])

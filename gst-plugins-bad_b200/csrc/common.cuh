@@ -72,6 +72,11 @@ static inline int b200vf_launched (b200vf_ctx *ctx, const char *name) {
   return B200VF_OK;
 }
 
+// host/gt_maps.cpp, for csrc/gt_device_maps.cu: the host's table entries for a list of pixels, and marble's tables
+int b200vf_gt_host_index_at (const char *element, int width, int height, const char *const *prop_names, const double *prop_values,
+    int nprops, int off_edge, const int32_t *pixels, size_t n, int32_t *index_out);
+int b200vf_gt_marble_tables (const char *const *prop_names, const double *prop_values, int nprops, double *out2054);
+
 // Small constant tables (LUTs, gaussian taps, colour tables) travel as
 // __grid_constant__ kernel parameters: no staging buffer, nothing to
 // synchronise, and the op stays asynchronous and stream-ordered.

@@ -279,7 +279,8 @@ int build_index (b200vf_element *e, const std::map<std::string, double> &P, cuda
   }
   int rc;
   if (b200vf_gt_device_map_supported (e->def->name) && !getenv ("B200VF_GT_HOST_MAPS")) {
-    // maps without libm calls are evaluated on the GPU, bit-identically (csrc/gt_device_maps.cu): no host rebuild, no upload
+    // evaluated on the GPU (csrc/gt_device_maps.cu): exactly for the maps without libm calls, certified entry by entry
+    // (the few uncertain ones patched in from the host) for the others: no host rebuild, no 4 B/px upload
     if (e->index_px != npx) {
       if (e->d_index) cudaFree (e->d_index);
       e->d_index = nullptr;
@@ -288,8 +289,10 @@ int build_index (b200vf_element *e, const std::map<std::string, double> &P, cuda
       if (rc) return rc;
       e->index_px = npx;
     }
-    return b200vf_gt_build_index_device (e->ctx, e->def->name, e->width, e->height, names.data (), values.data (), (int) names.size (),
+    rc = b200vf_gt_build_index_device (e->ctx, e->def->name, e->width, e->height, names.data (), values.data (), (int) names.size (),
         off_edge, e->d_index, s);
+    // a libm map too many of whose coordinates sit on integers (rotate at angle 0) cannot be certified: host table
+    if (rc != B200VF_E_UNSUPPORTED) return rc;
   }
   std::vector<double> map_xy (npx * 2);
   rc = b200vf_gt_build_map (e->def->name, e->width, e->height, names.data (), values.data (), (int) names.size (), map_xy.data ());

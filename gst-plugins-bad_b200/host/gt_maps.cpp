@@ -306,42 +306,44 @@ const std::vector<ElementDef> &elements () {
   return defs;
 }
 
-}  // namespace
-
-B200VF_API int b200vf_gt_build_map (const char *element, int width, int height, const char *const *prop_names,
-    const double *prop_values, int nprops, double *map_xy)
-{
-  B200VF_REQUIRE (element && map_xy && width > 0 && height > 0 && nprops >= 0, B200VF_E_INVAL, "gt_build_map: bad argument");
+// element + properties -> MapState (properties validated like a GObject setter would)
+struct BuiltState {
+  MapState s;
   const ElementDef *def = nullptr;
-  for (const auto &d : elements ()) if (!strcmp (d.name, element)) def = &d;
-  if (!def) {
+  Noise *noise = nullptr;
+  ~BuiltState () { delete noise; }
+};
+int make_state (BuiltState &b, const char *who, const char *element, int width, int height, const char *const *prop_names,
+    const double *prop_values, int nprops)
+{
+  for (const auto &d : elements ()) if (!strcmp (d.name, element)) b.def = &d;
+  if (!b.def) {
     if (!strcmp (element, "diffuse"))
-      b200vf_set_error ("gt_build_map: `diffuse` draws a fresh random map every frame (gstdiffuse.c:151-189); "
-          "it has no precalculated map and no bit-exact counterpart");
+      b200vf_set_error ("%s: `diffuse` draws a fresh random map every frame (gstdiffuse.c:151-189); "
+          "it has no precalculated map and no bit-exact counterpart", who);
     else
-      b200vf_set_error ("gt_build_map: unknown element `%s`", element);
+      b200vf_set_error ("%s: unknown element `%s`", who, element);
     return B200VF_E_UNSUPPORTED;
   }
-  MapState s;
+  MapState &s = b.s;
   s.width = width; s.height = height;
-  for (const auto &kv : def->defaults) s.prop[kv.first] = kv.second;
-  if (def->circle) { s.prop["x-center"] = 0.5; s.prop["y-center"] = 0.5; s.prop["radius"] = 0.35; }
+  for (const auto &kv : b.def->defaults) s.prop[kv.first] = kv.second;
+  if (b.def->circle) { s.prop["x-center"] = 0.5; s.prop["y-center"] = 0.5; s.prop["radius"] = 0.35; }
   for (int i = 0; i < nprops; i++) {
-    B200VF_REQUIRE (prop_names && prop_values && prop_names[i], B200VF_E_INVAL, "gt_build_map: NULL property");
+    B200VF_REQUIRE (prop_names && prop_values && prop_names[i], B200VF_E_INVAL, "gt map: NULL property");
     if (!strcmp (prop_names[i], "off-edge-pixels")) continue;    // a gather policy, not a map input
     auto it = s.prop.find (prop_names[i]);
     if (it == s.prop.end ()) {
-      b200vf_set_error ("gt_build_map: element `%s` has no property `%s`", element, prop_names[i]);
+      b200vf_set_error ("%s: element `%s` has no property `%s`", who, element, prop_names[i]);
       return B200VF_E_PROPERTY;
     }
     it->second = prop_values[i];
   }
-  if (def->circle) s.circle_precalc ();
-  for (size_t i = 0; i < def->defaults.size (); i++) s.v[i] = s.prop[def->defaults[i].first];
-  Noise *noise = nullptr;
+  if (b.def->circle) s.circle_precalc ();
+  for (size_t i = 0; i < b.def->defaults.size (); i++) s.v[i] = s.prop[b.def->defaults[i].first];
   if (!strcmp (element, "marble")) {                             // marble_prepare, gstmarble.c:160-183
-    noise = new Noise (0x9e3779b9u);
-    s.noise = noise;
+    b.noise = new Noise (0x9e3779b9u);
+    s.noise = b.noise;
     s.sin_table.resize (256); s.cos_table.resize (256);
     for (int i = 0; i < 256; i++) {
       double angle = (kPi * 2 * i) / 256.0 * s.get ("turbulence");
@@ -349,6 +351,35 @@ B200VF_API int b200vf_gt_build_map (const char *element, int width, int height, 
       s.cos_table[i] = s.get ("y-scale") * cos (angle);
     }
   }
+  return B200VF_OK;
+}
+
+// do_map's policy, truncation and bounds test for one pixel (gstgeometrictransform.c:167-207)
+inline int32_t resolve_one (double in_x, double in_y, int width, int height, int off_edge) {
+  if (off_edge == 1) {
+    in_x = clampd (in_x, 0, width - 1);
+    in_y = clampd (in_y, 0, height - 1);
+  } else if (off_edge == 2) {
+    in_x = mod_float (in_x, width);
+    in_y = mod_float (in_y, height);
+    if (in_x < 0) in_x += width;
+    if (in_y < 0) in_y += height;
+  }
+  int tx = (int) in_x, ty = (int) in_y;    // NaN / out-of-range -> INT_MIN on x86-64, like the reference build
+  return (tx >= 0 && tx < width && ty >= 0 && ty < height) ? ty * width + tx : -1;
+}
+
+}  // namespace
+
+B200VF_API int b200vf_gt_build_map (const char *element, int width, int height, const char *const *prop_names,
+    const double *prop_values, int nprops, double *map_xy)
+{
+  B200VF_REQUIRE (element && map_xy && width > 0 && height > 0 && nprops >= 0, B200VF_E_INVAL, "gt_build_map: bad argument");
+  BuiltState b;
+  int rc = make_state (b, "gt_build_map", element, width, height, prop_names, prop_values, nprops);
+  if (rc) return rc;
+  const MapState &s = b.s;
+  const ElementDef *def = b.def;
   // every pixel is independent: rows are split over the host cores (the reference builds its map
   // on one thread under the object lock, 3.6 s at 8K; the values do not depend on the split)
   unsigned nthreads = std::thread::hardware_concurrency ();
@@ -367,7 +398,37 @@ B200VF_API int b200vf_gt_build_map (const char *element, int width, int height, 
       pool.emplace_back (rows, (int) ((long long) height * t / nthreads), (int) ((long long) height * (t + 1) / nthreads));
     for (auto &th : pool) th.join ();
   }
-  delete noise;
+  return B200VF_OK;
+}
+
+// Internal (gt_device_maps.cu): the host's answer for a list of pixels - the entries the GPU evaluation could not
+// certify (a coordinate within its libm error bound of an integer).
+int b200vf_gt_host_index_at (const char *element, int width, int height, const char *const *prop_names, const double *prop_values,
+    int nprops, int off_edge, const int32_t *pixels, size_t n, int32_t *index_out)
+{
+  BuiltState b;
+  int rc = make_state (b, "gt_host_index_at", element, width, height, prop_names, prop_values, nprops);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; i++) {
+    const int x = pixels[i] % width, y = pixels[i] / width;
+    double ix, iy;
+    b.def->fn (b.s, x, y, &ix, &iy);
+    index_out[i] = resolve_one (ix, iy, width, height, off_edge);
+  }
+  return B200VF_OK;
+}
+
+// Internal (gt_device_maps.cu): marble's host-built tables (noise lattice from the fixed seed, sin / cos displacement
+// tables from glibc): p[514], g2[514][2], sin[256], cos[256] = 2054 doubles. The map over them needs no libm.
+int b200vf_gt_marble_tables (const char *const *prop_names, const double *prop_values, int nprops, double *out)
+{
+  BuiltState b;
+  int rc = make_state (b, "gt_marble_tables", "marble", 8, 8, prop_names, prop_values, nprops);
+  if (rc) return rc;
+  memcpy (out, b.noise->p, sizeof b.noise->p);
+  memcpy (out + 514, b.noise->g2, sizeof b.noise->g2);
+  memcpy (out + 514 + 1028, b.s.sin_table.data (), 256 * sizeof (double));
+  memcpy (out + 514 + 1028 + 256, b.s.cos_table.data (), 256 * sizeof (double));
   return B200VF_OK;
 }
 
@@ -379,20 +440,8 @@ B200VF_API int b200vf_gt_resolve_map (const double *map_xy, int width, int heigh
   B200VF_REQUIRE (off_edge >= 0 && off_edge <= 2, B200VF_E_PROPERTY, "gt_resolve_map: off-edge-pixels %d", off_edge);
   B200VF_REQUIRE ((long long) width * height < 0x7fffffffll, B200VF_E_INVAL, "gt_resolve_map: frame too large for int32 indices");
   const double *ptr = map_xy;
-  for (long long i = 0, n = (long long) width * height; i < n; i++, ptr += 2) {
-    double in_x = ptr[0], in_y = ptr[1];
-    if (off_edge == 1) {
-      in_x = clampd (in_x, 0, width - 1);
-      in_y = clampd (in_y, 0, height - 1);
-    } else if (off_edge == 2) {
-      in_x = mod_float (in_x, width);
-      in_y = mod_float (in_y, height);
-      if (in_x < 0) in_x += width;
-      if (in_y < 0) in_y += height;
-    }
-    int tx = (int) in_x, ty = (int) in_y;    // NaN / out-of-range -> INT_MIN on x86-64, like the reference build
-    index_out[i] = (tx >= 0 && tx < width && ty >= 0 && ty < height) ? ty * width + tx : -1;
-  }
+  for (long long i = 0, n = (long long) width * height; i < n; i++, ptr += 2)
+    index_out[i] = resolve_one (ptr[0], ptr[1], width, height, off_edge);
   return B200VF_OK;
 }
 

@@ -273,13 +273,21 @@ int b200vf_chromahold (b200vf_ctx *ctx, uint8_t *d_data, int width, int height, 
 int b200vf_gt_build_map (const char *element, int width, int height, const char *const *prop_names,
     const double *prop_values, int nprops, double *map_xy /* [height][width][2] */);
 int b200vf_gt_resolve_map (const double *map_xy, int width, int height, int off_edge, int32_t *index_out);
-/* The same table built ON the GPU, for the maps whose arithmetic is +, -, *, /, sqrt and comparisons only (mirror,
- * square, stretch, bulge, tunnel, perspective: b200vf_gt_device_map_supported): the kernel evaluates the reference's
- * fp64 expressions operation for operation (compiled without FMA contraction) and applies do_map's policy and
- * truncation, so d_index equals what b200vf_gt_build_map + b200vf_gt_resolve_map give - without the host rebuild
- * (0.2 s at 8K) and the 132 MB upload every time a GstController moves a property (needs_remap,
- * gstgeometrictransform.c:256-263). Maps that call libm stay on the host (B200VF_E_UNSUPPORTED here). */
+/* The same table built ON the GPU: d_index equals what b200vf_gt_build_map + b200vf_gt_resolve_map give - without the
+ * host rebuild (0.2 s at 8K) and the 132 MB upload every time a GstController moves a property (needs_remap,
+ * gstgeometrictransform.c:256-263). b200vf_gt_device_map_supported says how:
+ *   1  maps whose arithmetic is +, -, *, /, sqrt, comparisons and table lookups only (mirror, square, stretch, bulge,
+ *      tunnel, perspective, marble): the kernel evaluates the reference's fp64 expressions operation for operation
+ *      (compiled without FMA contraction); asynchronous on `stream`;
+ *   2  maps that call libm (fisheye, circle, kaleidoscope, pinch, rotate, sphere, twirl, waterripple): the kernel
+ *      evaluates with CUDA's libm and certifies every entry whose coordinates are further from an integer than a bound
+ *      on the disagreement with glibc; the others are evaluated by the host's map function and patched in. The call
+ *      synchronises `stream`. When more than 1/64 of the entries are uncertain (rotate at angle 0) it returns
+ *      B200VF_E_UNSUPPORTED and the caller builds the table on the host;
+ *   0  no such element (`diffuse`: per-frame random map).
+ * b200vf_gt_device_last_uncertain: how many entries the last build on this thread took from the host. */
 int b200vf_gt_device_map_supported (const char *element);
+long long b200vf_gt_device_last_uncertain (void);
 int b200vf_gt_build_index_device (b200vf_ctx *ctx, const char *element, int width, int height,
     const char *const *prop_names, const double *prop_values, int nprops, int off_edge, int32_t *d_index, void *stream);
 /* fill: 32-bit pattern the cleared frame holds (0, or 0x808010ff for AYUV =

@@ -110,7 +110,14 @@ def test_packed_fisheye_4k_equals_plain(ctx, vf, rng):
     assert np.array_equal(got, gpu_remap(ctx, vf, fr, idx, w, h, 4))
 
 
-DEVICE_MAPS = ("mirror", "square", "stretch", "bulge", "tunnel", "perspective")
+DEVICE_MAPS = ("mirror", "square", "stretch", "bulge", "tunnel", "perspective", "marble")
+LIBM_MAPS = ("fisheye", "circle", "kaleidoscope", "pinch", "rotate", "sphere", "twirl", "waterripple")
+MARBLE_CASES = [{}, {"x_scale": 7.0, "y_scale": 2.5, "turbulence": 3.0}]
+
+
+def device_cases(element):
+    import refprops
+    return MARBLE_CASES if element == "marble" else refprops.CASES[element]
 
 
 @pytest.mark.parametrize("element", DEVICE_MAPS)
@@ -118,10 +125,10 @@ DEVICE_MAPS = ("mirror", "square", "stretch", "bulge", "tunnel", "perspective")
 def test_device_built_index_equals_host_table(ctx, vf, element, w, h):
     """SURVEY 8f rank 3: the maps that need no libm are evaluated on the GPU in the reference's fp64 expression order;
     the int32 table must equal, entry for entry, the one resolved on the host from the (reference-bit-equal) double
-    map - for every property set of the parity tests and every off-edge policy."""
-    import refprops
-    assert vf.gt_device_map_supported(element)
-    for props in refprops.CASES[element]:
+    map - for every property set of the parity tests and every off-edge policy. (marble: libm-free once the host has
+    built its lattice / displacement tables.)"""
+    assert vf.gt_device_map_supported(element) == 1
+    for props in device_cases(element):
         m = vf.gt_build_map(element, w, h, props)
         for name, off in OFF.items():
             want = vf.gt_resolve_map(m, w, h, off)
@@ -133,18 +140,97 @@ def test_device_built_index_equals_host_table(ctx, vf, element, w, h):
 
 def test_device_built_index_at_4k_and_8k(ctx, vf):
     for (w, h) in [(3840, 2160), (7680, 4320)]:
-        for element, props in (("bulge", {"zoom": 7.5, "x_center": 0.3, "radius": 0.6}), ("square", {}), ("tunnel", {})):
+        for element, props in (("bulge", {"zoom": 7.5, "x_center": 0.3, "radius": 0.6}), ("square", {}), ("tunnel", {}), ("marble", {})):
             want = vf.gt_resolve_map(vf.gt_build_map(element, w, h, props), w, h, 1)
             got = ctx.download(vf.gt_build_index_device(ctx, element, w, h, props, 1), w * h * 4, dtype=np.int32)
             assert np.array_equal(got, want.reshape(-1)), (element, w)
 
 
-def test_libm_maps_stay_on_the_host(ctx, vf):
-    for element in ("fisheye", "circle", "kaleidoscope", "pinch", "rotate", "sphere", "twirl", "waterripple", "marble"):
-        assert not vf.gt_device_map_supported(element)
+def build_certified(ctx, vf, element, w, h, props, off):
+    """the device table, or None when the build reports that it cannot certify the map"""
+    try:
+        d = vf.gt_build_index_device(ctx, element, w, h, props, off)
+    except vf.B200vfError as err:
+        assert err.status == vf.E_UNSUPPORTED, err
+        return None
+    return ctx.download(d, w * h * 4, dtype=np.int32).reshape(h, w)
+
+
+@pytest.mark.parametrize("element", LIBM_MAPS)
+@pytest.mark.parametrize("w,h", [(64, 48), (100, 75), (257, 131)])
+def test_certified_libm_tables_equal_host_tables(ctx, vf, element, w, h):
+    """The maps that call libm: CUDA's pow / atan2 / sin ... differ from glibc's in the last ulps and do_map truncates, so
+    the kernel certifies each entry (coordinate further from an integer than a bound on the disagreement) and takes the
+    others from the host's map function. The patched table must equal the host's, entry for entry; the only property
+    set the build may refuse is rotate at angle 0, where EVERY coordinate sits within 1e-13 of an integer."""
+    import refprops
+    assert vf.gt_device_map_supported(element) == 2
+    for props in refprops.CASES[element]:
+        m = vf.gt_build_map(element, w, h, props)
+        for name, off in OFF.items():
+            want = vf.gt_resolve_map(m, w, h, off).reshape(h, w)
+            got = build_certified(ctx, vf, element, w, h, props, off)
+            if got is None:
+                assert element == "rotate" and not props, (element, props)
+                continue
+            assert vf.gt_device_last_uncertain() <= max(4096, w * h // 64)
+            assert np.array_equal(got, want), (element, props, name, np.argwhere(got != want)[:5])
+
+
+def test_certified_libm_tables_over_random_properties(ctx, vf):
+    """a seeded sweep over the property ranges of the libm maps (incl. refraction < 1, where sphere's asin leaves its
+    domain, negative pinch intensities, the angle wrap of circle) at a size whose centre is not a pixel"""
+    import refprops
+    rng = np.random.default_rng(7)
+    w, h = 321, 203
+    ranges = {
+        "circle": {"angle": (-3.2, 3.2), "spread_angle": (0.2, 6.3), "height": (1, 80), "x_center": (0, 1), "y_center": (0, 1), "radius": (0, 1)},
+        "kaleidoscope": {"angle": (-3.2, 3.2), "angle2": (-3.2, 3.2), "sides": (2, 9), "x_center": (0, 1), "radius": (0, 1)},
+        "pinch": {"intensity": (-1, 1), "x_center": (0, 1), "y_center": (0, 1), "radius": (0.05, 1)},
+        "rotate": {"angle": (-6.3, 6.3)},
+        "sphere": {"refraction": (0.3, 3.0), "x_center": (0, 1), "radius": (0.05, 1)},
+        "twirl": {"angle": (-6.3, 6.3), "y_center": (0, 1), "radius": (0.05, 1)},
+        "waterripple": {"amplitude": (-40, 40), "phase": (-7, 7), "wavelength": (2, 60), "x_center": (0, 1), "radius": (0.05, 1)},
+    }
+    refused = 0
+    for element, rr in ranges.items():
+        for trial in range(6):
+            props = {k: (float(np.floor(rng.uniform(*v))) if k in ("sides", "height") else float(rng.uniform(*v))) for k, v in rr.items()}
+            off = int(rng.integers(0, 3))
+            want = vf.gt_resolve_map(vf.gt_build_map(element, w, h, props), w, h, off).reshape(h, w)
+            got = build_certified(ctx, vf, element, w, h, props, off)
+            if got is None:
+                refused += 1
+                continue
+            assert np.array_equal(got, want), (element, props, off, np.argwhere(got != want)[:5])
+    assert refused <= 4, refused
+
+
+def test_certified_libm_tables_at_4k_and_8k(ctx, vf):
+    """fisheye (BASELINE configs[3]) and three more at the BASELINE sizes; how many entries the host had to supply"""
+    for (w, h) in [(3840, 2160), (7680, 4320)]:
+        for element, props in (("fisheye", {}), ("twirl", {"angle": -2.0}), ("sphere", {}), ("kaleidoscope", {"sides": 7, "x_center": 0.25})):
+            want = vf.gt_resolve_map(vf.gt_build_map(element, w, h, props), w, h, 1)
+            got = ctx.download(vf.gt_build_index_device(ctx, element, w, h, props, 1), w * h * 4, dtype=np.int32)
+            assert np.array_equal(got, want.reshape(-1)), (element, w)
+            assert vf.gt_device_last_uncertain() < w * h // 256, (element, vf.gt_device_last_uncertain())
+
+
+def test_uncertifiable_map_falls_back_to_the_host_table(ctx, vf, orc, rng):
+    """rotate at its default angle 0: the build refuses, the element builds the table on the host, the frame is the reference's"""
+    w, h = 160, 120
     with pytest.raises(vf.B200vfError) as err:
-        vf.gt_build_index_device(ctx, "twirl", 64, 48)
-    assert err.value.status == vf.E_UNSUPPORTED
+        vf.gt_build_index_device(ctx, "rotate", w, h)
+    assert err.value.status == vf.E_UNSUPPORTED and vf.gt_device_last_uncertain() > w * h // 64
+    with pytest.raises(vf.B200vfError):
+        vf.gt_build_index_device(ctx, "diffuse", w, h)
+    assert vf.gt_device_map_supported("diffuse") == 0
+    fr = frames.random_u8(rng, h, 4 * w)
+    e = ctx.element("rotate")
+    e.set_caps("RGBA", "RGBA", w, h)
+    got = e.transform(fr).reshape(h, 4 * w)
+    policy = {v: k for k, v in OFF.items()}[int(e.get_property("off-edge-pixels"))]
+    assert np.array_equal(got, orc.remap(fr, vf.gt_build_map("rotate", w, h), w, h, 4, policy, False))
 
 
 def test_element_rebuilds_its_table_on_the_gpu_when_a_property_moves(ctx, vf, orc, rng, monkeypatch):
