@@ -104,6 +104,11 @@ _SIGS = {
     "b200vf_gt_build_index_device": (_i, [_vp, C.c_char_p, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "b200vf_gt_resolve_map": (_i, [_vp, _i, _i, _i, _vp]),
     "b200vf_remap": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _sz, _i, _u32, _vp]),
+    "b200vf_diffuse_draw": (None, [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_i), C.POINTER(C.c_double)]),
+    "b200vf_diffuse_tables": (_i, [C.c_double, _vp, _vp]),
+    "b200vf_diffuse": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _sz, _sz, _i, _vp, _vp, _i, _u32, C.c_uint64, C.c_uint64, _vp]),
+    "b200vf_element_set_rng_seed": (_i, [_vp, C.c_uint64, C.c_uint64]),
+    "b200vf_element_get_rng_state": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "b200vf_gt_packed_bound": (_sz, [_i, _i]),
     "b200vf_gt_pack_index": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz)]),
     "b200vf_gt_unpack_index": (_i, [_vp, _sz, _i, _i, _vp]),
@@ -404,6 +409,15 @@ class Context:
         check(lib.b200vf_remap(self.h, _ptr(src), _ptr(dst), _ptr(index), width, height, pixel_stride, row_stride,
                                row_stride * height, nframes, fill, stream))
 
+    def diffuse(self, src, dst, width, height, pixel_stride, row_stride, sin_table, cos_table, off_edge=1, fill=0, seed=0,
+                first_frame=0, nframes=1, first_row=0, full_height=None, stream=None):
+        full_height = height if full_height is None else full_height
+        st = np.ascontiguousarray(sin_table, np.float64)
+        ct = np.ascontiguousarray(cos_table, np.float64)
+        check(lib.b200vf_diffuse(self.h, _ptr(src), _ptr(dst), width, height, first_row, full_height, pixel_stride, row_stride,
+                                 row_stride * full_height, row_stride * height, nframes, _hptr(st), _hptr(ct), off_edge, fill,
+                                 seed, first_frame, stream))
+
     def remap_packed(self, src, dst, packed, width, height, fill=0, nframes=1, stream=None):
         check(lib.b200vf_remap_packed(self.h, _ptr(src), _ptr(dst), _ptr(packed), width, height, 4 * width * height,
                                       nframes, fill, stream))
@@ -601,6 +615,19 @@ def gt_build_map(element, width, height, props=None):
     m = np.zeros((height, width, 2), np.float64)
     check(lib.b200vf_gt_build_map(element.encode(), width, height, cn, cv, n, _hptr(m)))
     return m
+
+
+def diffuse_draw(seed, frame, pixel):
+    """(angle 0..255, distance in [0, 1)) pixel `pixel` of frame `frame` draws: the generator of csrc/diffuse.cu on the host"""
+    a, d = _i(), C.c_double()
+    lib.b200vf_diffuse_draw(seed, frame, pixel, C.byref(a), C.byref(d))
+    return a.value, d.value
+
+
+def diffuse_tables(scale):
+    s, c = np.zeros(256, np.float64), np.zeros(256, np.float64)
+    check(lib.b200vf_diffuse_tables(scale, _hptr(s), _hptr(c)))
+    return s, c
 
 
 def gt_device_map_supported(element):
@@ -824,6 +851,14 @@ class Element:
 
     def transform_device(self, d_in, d_out, nframes=1, stream=None):
         check(lib.b200vf_element_transform_device(self.h, _ptr(d_in), _ptr(d_out), nframes, stream))
+
+    def set_rng_seed(self, seed, next_frame=0):
+        check(lib.b200vf_element_set_rng_seed(self.h, seed, next_frame))
+
+    def rng_state(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        check(lib.b200vf_element_get_rng_state(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def last_values(self):
         v = (C.c_double * 8)()

@@ -26,6 +26,7 @@
 // 16 KB of lattice and displacement tables, and joins the exact set.
 //
 #include "common.cuh"
+#include "gt_resolve.cuh"
 #include <string.h>
 #include <math.h>
 #include <vector>
@@ -42,34 +43,9 @@ struct DevMap {
   const double *tables;                 // marble: p[514], g2[514][2], sin[256], cos[256]
 };
 
-__device__ __forceinline__ double clampd (double x, double lo, double hi) { return (x > hi) ? hi : ((x < lo) ? lo : x); }   // CLAMP
-// (int) of a double as the reference's x86-64 build evaluates it (cvttsd2si): NaN and out-of-range give INT_MIN
-__device__ __forceinline__ int d2i (double x) { return (x > -2147483649.0 && x < 2147483648.0) ? (int) x : (int) 0x80000000; }
-// geometricmath.c:171-180
-__device__ __forceinline__ double mod_float (double a, double b) {
-  int n = d2i (a / b);
-  a -= n * b;
-  if (a < 0) return a + b;
-  return a;
-}
 __device__ __forceinline__ double smoothstep (double e0, double e1, double x) {
   double t = clampd ((x - e0) / (e1 - e0), 0.0, 1.0);
   return t * t * (3.0 - 2.0 * t);
-}
-
-// do_map's policy, truncation and bounds test (gstgeometrictransform.c:167-207), as gt_maps.cpp's resolve_one
-__device__ __forceinline__ int32_t resolve_one (double ix, double iy, int width, int height, int off_edge) {
-  if (off_edge == 1) {
-    ix = clampd (ix, 0, width - 1);
-    iy = clampd (iy, 0, height - 1);
-  } else if (off_edge == 2) {
-    ix = mod_float (ix, width);
-    iy = mod_float (iy, height);
-    if (ix < 0) ix += width;
-    if (iy < 0) iy += height;
-  }
-  const int tx = d2i (ix), ty = d2i (iy);
-  return (tx >= 0 && tx < width && ty >= 0 && ty < height) ? ty * width + tx : -1;
 }
 
 __global__ void __launch_bounds__ (256)

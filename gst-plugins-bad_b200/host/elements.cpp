@@ -154,6 +154,8 @@ const std::vector<FactoryDef> &factories () {
         { "matrix-2", P_DOUBLE, -kMaxD, kMaxD, 0, {} }, { "matrix-3", P_DOUBLE, -kMaxD, kMaxD, 0, {} }, { "matrix-4", P_DOUBLE, -kMaxD, kMaxD, 1, {} },
         { "matrix-5", P_DOUBLE, -kMaxD, kMaxD, 0, {} }, { "matrix-6", P_DOUBLE, -kMaxD, kMaxD, 0, {} }, { "matrix-7", P_DOUBLE, -kMaxD, kMaxD, 0, {} },
         { "matrix-8", P_DOUBLE, -kMaxD, kMaxD, 1, {} } }), false, 0 },
+    // gstdiffuse.c:213-231: no precalculated map (a fresh random displacement per pixel and frame)
+    { "diffuse", K_GEOMETRIC, kGeo, geo (1, false, { { "scale", P_DOUBLE, 1.0, kMaxD, 4.0, {} } }), false, 1 },
     { "marble", K_GEOMETRIC, kGeo, geo (1, false, { { "x-scale", P_DOUBLE, 0, kMaxD, 4, {} }, { "y-scale", P_DOUBLE, 0, kMaxD, 4, {} },
         { "amount", P_DOUBLE, 0.0, 1.0, 1, {} }, { "turbulence", P_DOUBLE, 0.0, 1.0, 1, {} } }), false, 1 },
     // videofiltersbad (gstvideofiltersbad.c:33-41); SURVEY 8f rank 4
@@ -207,6 +209,11 @@ struct b200vf_element {
   bool need_remap = true;
   int32_t *d_index = nullptr;
   size_t index_px = 0;
+  // diffuse: displacement tables (built by the first negotiation and kept: diffuse_prepare returns early once they
+  // exist, gstdiffuse.c:156-157 - later changes of `scale` never reach them), generator seed, frames drawn so far
+  bool diffuse_prepared = false;
+  double diffuse_sin[256], diffuse_cos[256];
+  uint64_t rng_seed = 0x6a09e667f3bcc908ull, rng_frame = 0;
   // videofiltersbad: luma geometry, zebrastripe's frame counter, the previous frame's luma plane (videodiff,
   // scenechange keep a reference to the previous buffer: gstvideodiff.c:168-169, gstscenechange.c:193-194)
   const YuvDef *yuv = nullptr;
@@ -325,6 +332,7 @@ bool claim_remap (b200vf_element *e, std::map<std::string, double> &P) {
   return need;
 }
 int rebuild_index_if_needed (b200vf_element *e, cudaStream_t s) {
+  if (!strcmp (e->def->name, "diffuse")) return B200VF_OK;     // precalc_map = FALSE (gstdiffuse.c:228): no table
   std::map<std::string, double> P;
   if (!claim_remap (e, P)) return B200VF_OK;
   int rc = build_index (e, P, s);
@@ -532,6 +540,17 @@ int run (b200vf_element *e, const uint8_t *d_in, uint8_t *d_out, int nframes, cu
       return B200VF_OK;
     }
     case K_GEOMETRIC: {
+      if (!strcmp (e->def->name, "diffuse")) {
+        uint32_t fill = !strcmp (e->fmt->name, "AYUV") ? 0x808010ffu : 0u;
+        uint64_t first;
+        {
+          std::lock_guard<std::mutex> g (e->lock);
+          first = e->rng_frame;
+          e->rng_frame += (uint64_t) nframes;
+        }
+        return b200vf_diffuse (ctx, d_in, d_out, w, h, 0, h, e->fmt->pstride, e->in_stride, e->in_bytes, e->in_bytes, nframes, e->diffuse_sin,
+            e->diffuse_cos, (int) P["off-edge-pixels"], fill, e->rng_seed, first, s);
+      }
       int rc = rebuild_index_if_needed (e, s);
       if (rc) return rc;
       uint32_t fill = !strcmp (e->fmt->name, "AYUV") ? 0x808010ffu : 0u;     // GST_WRITE_UINT32_BE (.., 0xff108080), :244-250
@@ -557,10 +576,7 @@ B200VF_API int b200vf_element_factory_make (b200vf_ctx *ctx, const char *factory
     *out = e;
     return B200VF_OK;
   }
-  if (!strcmp (factory, "diffuse"))
-    b200vf_set_error ("no element `diffuse`: it draws a fresh random map every frame and has no deterministic counterpart");
-  else
-    b200vf_set_error ("no such element factory `%s`", factory);
+  b200vf_set_error ("no such element factory `%s`", factory);
   return B200VF_E_UNSUPPORTED;
 }
 
@@ -675,6 +691,13 @@ B200VF_API int b200vf_element_set_caps (b200vf_element *e, const char *in_format
     e->in_bytes = e->out_bytes = (size_t) e->in_stride * height;
   }
   if (width != e->width || height != e->height) { std::lock_guard<std::mutex> g (e->lock); e->need_remap = true; }
+  if (!strcmp (e->def->name, "diffuse") && !e->diffuse_prepared) {
+    // set_info calls prepare_func (gstgeometrictransform.c:152-157); diffuse's builds its tables only the first time
+    std::lock_guard<std::mutex> g (e->lock);
+    int rc = b200vf_diffuse_tables (e->props["scale"], e->diffuse_sin, e->diffuse_cos);
+    if (rc) return rc;
+    e->diffuse_prepared = true;
+  }
   e->width = width;
   e->height = height;
   e->negotiated = true;
@@ -1102,4 +1125,23 @@ B200VF_API const char *b200vf_factory_format (const char *factory, int index) {
   for (const auto &f : factories ())
     if (!strcmp (f.name, factory)) return (index >= 0 && index < (int) f.formats.size ()) ? f.formats[index] : nullptr;
   return nullptr;
+}
+
+// diffuse: the reference draws from GLib's global generator (seeded by the OS); here the generator is a function of
+// (seed, frame, pixel) (csrc/diffuse.cu): an application that wants a different texture per run sets its own seed.
+B200VF_API int b200vf_element_set_rng_seed (b200vf_element *e, uint64_t seed, uint64_t next_frame) {
+  B200VF_REQUIRE (e, B200VF_E_INVAL, "element_set_rng_seed: NULL element");
+  B200VF_REQUIRE (!strcmp (e->def->name, "diffuse"), B200VF_E_UNSUPPORTED, "%s draws no random numbers", e->def->name);
+  std::lock_guard<std::mutex> g (e->lock);
+  e->rng_seed = seed;
+  e->rng_frame = next_frame;
+  return B200VF_OK;
+}
+B200VF_API int b200vf_element_get_rng_state (b200vf_element *e, uint64_t *seed, uint64_t *next_frame) {
+  B200VF_REQUIRE (e && seed && next_frame, B200VF_E_INVAL, "element_get_rng_state: NULL argument");
+  B200VF_REQUIRE (!strcmp (e->def->name, "diffuse"), B200VF_E_UNSUPPORTED, "%s draws no random numbers", e->def->name);
+  std::lock_guard<std::mutex> g (e->lock);
+  *seed = e->rng_seed;
+  *next_frame = e->rng_frame;
+  return B200VF_OK;
 }

@@ -267,7 +267,7 @@ int b200vf_chromahold (b200vf_ctx *ctx, uint8_t *d_data, int width, int height, 
  * (ty*width+tx, or -1 = keep the fill value) with exactly do_map's off-edge
  * policy and truncation, and the kernel gathers.
  *   element: "fisheye" "circle" ... (the 16 factory names of plugin.c:40-62,
- *   `diffuse` excluded: per-frame RNG). props: element properties as name/value
+ *   `diffuse` excluded: it has no precalculated map, see b200vf_diffuse). props: element properties as name/value
  *   pairs ("x-center", "zoom", ...; enum/int properties as doubles).
  *   off_edge: 0 ignore, 1 clamp, 2 wrap (enum :57-75). */
 int b200vf_gt_build_map (const char *element, int width, int height, const char *const *prop_names,
@@ -284,12 +284,27 @@ int b200vf_gt_resolve_map (const double *map_xy, int width, int height, int off_
  *      on the disagreement with glibc; the others are evaluated by the host's map function and patched in. The call
  *      synchronises `stream`. When more than 1/64 of the entries are uncertain (rotate at angle 0) it returns
  *      B200VF_E_UNSUPPORTED and the caller builds the table on the host;
- *   0  no such element (`diffuse`: per-frame random map).
+ *   0  no table for this element (`diffuse` draws per frame: b200vf_diffuse).
  * b200vf_gt_device_last_uncertain: how many entries the last build on this thread took from the host. */
 int b200vf_gt_device_map_supported (const char *element);
 long long b200vf_gt_device_last_uncertain (void);
 int b200vf_gt_build_index_device (b200vf_ctx *ctx, const char *element, int width, int height,
     const char *const *prop_names, const double *prop_values, int nprops, int off_edge, int32_t *d_index, void *stream);
+/* diffuse (gstdiffuse.c:151-231): the one element without a precalculated map - every pixel of every frame draws an
+ * angle (0..255) and a distance in [0, 1) and copies the pixel at (x + distance * sin_table[angle],
+ * y + distance * cos_table[angle]) under do_map's policy. The reference draws from GLib's global generator, so no two
+ * runs of it agree (parity unpinned by construction); here the draw is a stateless function of (seed, frame number,
+ * pixel number = y * width + x), the same on host (b200vf_diffuse_draw) and device, and everything around it - fp64
+ * arithmetic with separately rounded multiply and add, policy, truncation, bounds, the cleared frame - is the
+ * reference's. b200vf_diffuse_tables = diffuse_prepare (:151-165) with the host's libm. Rows [first_row,
+ * first_row + height) of a full_height frame are written (d_dst points at row first_row); d_src is the whole frame.
+ * Frame f of the call draws with frame number first_frame + f. */
+void b200vf_diffuse_draw (uint64_t seed, uint64_t frame, uint64_t pixel, int *angle, double *distance);
+int b200vf_diffuse_tables (double scale, double *sin_table /* [256] */, double *cos_table /* [256] */);
+int b200vf_diffuse (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, int width, int height, int first_row,
+    int full_height, int pixel_stride, int row_stride, size_t src_frame_stride, size_t dst_frame_stride, int nframes,
+    const double *sin_table, const double *cos_table, int off_edge, uint32_t fill, uint64_t seed, uint64_t first_frame,
+    void *stream);
 /* fill: 32-bit pattern the cleared frame holds (0, or 0x808010ff for AYUV =
  * GST_WRITE_UINT32_BE(0xff108080), :244-252); pixel_stride 1,2,3 or 4. */
 int b200vf_remap (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d_dst, const int32_t *d_index,
@@ -515,6 +530,9 @@ int b200vf_element_last_events (const b200vf_element *e, int *flags, int capacit
  * data) - of the last frame transformed: the fields of the element messages the reference posts
  * (gstvideoanalyse.c:178-204, gstsimplevideomarkdetect.c:352-389). Returns how many values there are. */
 int b200vf_element_last_values (const b200vf_element *e, double *values, int capacity);
+/* diffuse only: the seed of its draws and the frame number the next frame draws with (defaults: a fixed seed, 0) */
+int b200vf_element_set_rng_seed (b200vf_element *e, uint64_t seed, uint64_t next_frame);
+int b200vf_element_get_rng_state (b200vf_element *e, uint64_t *seed, uint64_t *next_frame);
 
 /* ------------------------------------------------- factory introspection
  * What gst-inspect prints for each element, so that the C/GLib shells (gst/gstb200vf.c) can register the

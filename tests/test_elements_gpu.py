@@ -137,7 +137,7 @@ def test_property_and_caps_errors(ctx, vf):
         e.set_caps("AYUV", "AYUV", 8, 8)
     assert err.value.status == vf.E_UNSUPPORTED
     with pytest.raises(vf.B200vfError) as err:
-        ctx.element("diffuse")
+        ctx.element("no-such-element")
     assert err.value.status == vf.E_UNSUPPORTED
 
 

@@ -171,10 +171,6 @@ def test_element_surface_matches_reference_api_dump(vf):
     reference (fixture extracted by tests/golden/make_golden.py); pad-template formats too."""
     surf = json.load(open(os.path.join(ROOT, "tests", "golden", "element_surface.json")))
     for name, el in surf.items():
-        if name == "diffuse":
-            with pytest.raises(vf.B200vfError):
-                vf.Element(None, name)
-            continue
         e = vf.Element(None, name)                          # no device needed to inspect an element
         for pn, pd in el["properties"].items():
             if pd["type"] == "GValueArray":                 # perspective's 3x3 matrix: exposed as matrix-0..8
@@ -240,7 +236,7 @@ def test_factory_introspection_matches_reference_api_dump(vf):
     klass, long name, description, author, controllable flags == the reference's docs/plugins/gst_plugins_cache.json"""
     surf = json.load(open(os.path.join(ROOT, "tests", "golden", "element_surface.json")))
     fac = vf.factories()
-    assert set(fac) == set(surf) - {"diffuse"}
+    assert set(fac) == set(surf)
     for name, f in fac.items():
         e = surf[name]
         assert f["plugin"] == e["plugin"] and f["type_name"] == e["hierarchy"][0] and f["parent_type_name"] == e["hierarchy"][1]
