@@ -744,6 +744,24 @@ def side_measurements(ctx, torch, b200vf, st, side, peak):
             t = timeit(lambda: ctx.remap_packed(a, b, d_packed, w, h, nframes=n4, stream=st))
             rec("fisheye_8k_remap_packed", n4, px, 8, t, {"host_pack_s": t_pack, "raw_groups": raw_groups,
                                                           "index_table_bytes_per_px": packed.size / px})
+            cnt[0] = 0
+
+            def one_packed():
+                i = cnt[0] % ring
+                cnt[0] += 1
+                ctx.remap_packed(a[i], b[i], d_packed, w, h, nframes=1, stream=st)
+            t1p = timeit(one_packed, iters=2 * ring)
+            rec("fisheye_8k_remap_packed_single_frame", 1, px, 8, t1p, {"index_table_bytes_per_px": packed.size / px,
+                                                                         "note": "one frame per launch, ring of %d frames" % ring})
+            # diffuse: no table at all - every pixel of every frame draws its displacement (csrc/diffuse.cu)
+            st_, ct_ = b200vf.diffuse_tables(4.0)
+            fcount = [0]
+
+            def diffuse_step():
+                ctx.diffuse(a, b, w, h, 4, 4 * w, st_, ct_, 1, 0, 1, fcount[0], nframes=n4, stream=st)
+                fcount[0] += n4
+            t = timeit(diffuse_step)
+            rec("diffuse_8k", n4, px, 8, t, {"note": "per-pixel, per-frame draws + gather; scale 4, clamp"})
         del a, b, dst
     return out
 
