@@ -14,7 +14,7 @@
 // every thread computes its own without state, a frame can be recomputed anywhere (b200vf_diffuse_draw is the same
 // function on the host; tests rebuild whole frames from it and push them through the reference's do_map), and a
 // row-sharded frame draws the same numbers whichever GPU owns the row. Statistics of the draws (uniform angle over
-// 256 values, uniform distance in [0, 1) with 53 bits): tests/test_diffuse_gpu.py.
+// 256 values, uniform distance in [0, 1) with 52 bits): tests/test_diffuse_gpu.py.
 #include "common.cuh"
 #include "gt_resolve.cuh"
 
@@ -29,7 +29,11 @@ __host__ __device__ __forceinline__ uint64_t diffuse_bits (uint64_t seed, uint64
 }
 __host__ __device__ __forceinline__ int diffuse_angle (uint64_t z) { return (int) (z >> 56); }                       // g_random_int_range (0, 256)
 __host__ __device__ __forceinline__ double diffuse_distance (uint64_t z) {                                           // g_random_double (): [0, 1)
-  return (double) ((z >> 3) & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
+  // bits 4..55 as the mantissa of a double in [1, 2), minus 1: k / 2^52, exact, and no 64-bit int -> double conversion
+  const uint64_t bits = 0x3FF0000000000000ull | ((z >> 4) & 0x000FFFFFFFFFFFFFull);
+  double d;
+  memcpy (&d, &bits, sizeof d);
+  return d - 1.0;
 }
 
 struct DiffuseParams {
@@ -40,36 +44,55 @@ struct DiffuseParams {
   uint64_t seed, first_frame;
 };
 
-// one output pixel per thread; rows [first_row, first_row + height) of a full_height frame (row shards draw the
-// numbers of their global pixel positions); the source is the whole frame
+// A block takes DPX consecutive pixels of one output row, thread t the pixels t, 256 + t, ... (coalesced stores);
+// rows [first_row, first_row + height) of a full_height frame (row shards draw the numbers of their global pixel
+// positions); the source is the whole frame. The displacement tables are staged in shared memory: indexed by a random
+// angle they would serialise 32-fold in the constant bank (first version: 0.017 of the HBM peak).
+constexpr int DPX = 1024;
 template <bool WORDS> __global__ void __launch_bounds__ (256)
 diffuse_kernel (const __grid_constant__ DiffuseParams p, const uint8_t *__restrict__ src, uint8_t *__restrict__ dst)
 {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, yl = blockIdx.y, y = p.first_row + yl;
+  __shared__ double2 s_tab[256];                 // (sin, cos): one 128-bit lookup per pixel
+  s_tab[threadIdx.x] = make_double2 (p.sin_table[threadIdx.x], p.cos_table[threadIdx.x]);
+  __syncthreads ();
   const uint8_t *s = src + (size_t) blockIdx.z * p.src_frame_stride;
-  uint8_t *d = dst + (size_t) blockIdx.z * p.dst_frame_stride + (size_t) yl * p.row_stride;
-  if (x < p.width) {
-    const uint64_t z = diffuse_bits (p.seed, p.first_frame + blockIdx.z, (uint64_t) y * p.width + x);
-    const int angle = diffuse_angle (z);
-    const double distance = diffuse_distance (z);
-    const double in_x = x + distance * p.sin_table[angle];
-    const double in_y = y + distance * p.cos_table[angle];
-    const int ix = resolve_one (in_x, in_y, p.width, p.full_height, p.off_edge);
-    if (WORDS) {
-      const uint32_t v = ix >= 0 ? __ldg (reinterpret_cast<const uint32_t *> (s + (size_t) (ix / p.width) * p.row_stride) + ix % p.width) : p.fill;
-      st_stream_u32 (d + (size_t) x * 4, v);
-    } else {
-      uint8_t *o = d + (size_t) x * p.ps;
-      if (ix >= 0) {
-        const uint8_t *in = s + (size_t) (ix / p.width) * p.row_stride + (size_t) (ix % p.width) * p.ps;
-        for (int b = 0; b < p.ps; b++) o[b] = in[b];
+  const uint64_t frame = p.first_frame + blockIdx.z;
+  const int x0 = blockIdx.x * DPX + threadIdx.x;
+  // the block walks down its column of the frame: the 4 KB of tables are staged once, not once per 1024 pixels
+  // (indexed per lane, the constant bank serialises: the staging was 20 % of the warp time with one row per block)
+  for (int yl = blockIdx.y; yl < p.height; yl += gridDim.y) {
+    const int y = p.first_row + yl;
+    uint8_t *d = dst + (size_t) blockIdx.z * p.dst_frame_stride + (size_t) yl * p.row_stride;
+    const double yd = y;
+    double xd = x0;                              // one int -> double conversion per thread and row, then exact additions
+#pragma unroll
+    for (int j = 0; j < DPX / 256; j++, xd += 256.0) {
+      const int x = x0 + j * 256;
+      if (x >= p.width) break;
+      const uint64_t z = diffuse_bits (p.seed, frame, (uint64_t) y * p.width + x);
+      const double2 sc = s_tab[diffuse_angle (z)];
+      const double distance = diffuse_distance (z);
+      const double in_x = xd + distance * sc.x;
+      const double in_y = yd + distance * sc.y;
+      int tx, ty;
+      const bool mapped = resolve_xy (in_x, in_y, p.width, p.full_height, p.off_edge, tx, ty);
+      if (WORDS) {
+        const uint32_t v = mapped ? __ldg (reinterpret_cast<const uint32_t *> (s + (size_t) ty * p.row_stride) + tx) : p.fill;
+        st_stream_u32 (d + (size_t) x * 4, v);
       } else {
-        for (int b = 0; b < p.ps; b++) o[b] = (uint8_t) (p.fill >> (8 * ((x * p.ps + b) & 3)));
+        uint8_t *o = d + (size_t) x * p.ps;
+        if (mapped) {
+          const uint8_t *in = s + (size_t) ty * p.row_stride + (size_t) tx * p.ps;
+          for (int b = 0; b < p.ps; b++) o[b] = in[b];
+        } else {
+          for (int b = 0; b < p.ps; b++) o[b] = (uint8_t) (p.fill >> (8 * ((x * p.ps + b) & 3)));
+        }
       }
     }
+    // row padding belongs to the cleared frame (memset covers map[0].size)
+    if (blockIdx.x == 0)
+      for (int b = p.width * p.ps + threadIdx.x; b < p.row_stride; b += blockDim.x) d[b] = (uint8_t) (p.fill >> (8 * (b & 3)));
   }
-  // row padding belongs to the cleared frame (memset covers map[0].size)
-  for (int b = p.width * p.ps + x; b < p.row_stride; b += gridDim.x * blockDim.x) d[b] = (uint8_t) (p.fill >> (8 * (b & 3)));
 }
 
 }  // namespace
@@ -99,7 +122,10 @@ B200VF_API int b200vf_diffuse (b200vf_ctx *ctx, const uint8_t *d_src, uint8_t *d
   p.width = width; p.height = height; p.ps = pixel_stride; p.row_stride = row_stride; p.off_edge = off_edge;
   p.first_row = first_row; p.full_height = full_height;
   p.src_frame_stride = src_frame_stride; p.dst_frame_stride = dst_frame_stride; p.fill = fill; p.seed = seed; p.first_frame = first_frame;
-  dim3 grid ((width + 255) / 256, height, nframes);
+  const int gx = (width + DPX - 1) / DPX;
+  long long gy = (long long) ctx->sm_count * 10 / ((long long) gx * nframes);          // ~10 blocks per SM over the whole launch
+  gy = gy < 1 ? 1 : (gy > height ? height : gy);
+  dim3 grid (gx, (unsigned) gy, nframes);
   const bool words = pixel_stride == 4 && row_stride % 4 == 0 && src_frame_stride % 4 == 0 && dst_frame_stride % 4 == 0 && ((uintptr_t) d_src) % 4 == 0 && ((uintptr_t) d_dst) % 4 == 0;
   if (words) diffuse_kernel<true><<<grid, 256, 0, s>>> (p, d_src, d_dst);
   else diffuse_kernel<false><<<grid, 256, 0, s>>> (p, d_src, d_dst);

@@ -283,8 +283,10 @@ B200VF_API int b200vf_remap_packed (b200vf_ctx *ctx, const uint8_t *d_src, uint8
   cudaStream_t s = b200vf_stream (ctx, stream);
   const PackedLayout L = packed_layout (width, height);
   const uint8_t *base = static_cast<const uint8_t *> (d_packed);
-  int per_sm = 1;                                                         // blocks per SM (sweep in profiles/: 1 is best, 20.2k fps at 8K; more resident warps only spread the gathers)
-  if (const char *e = getenv ("B200VF_REMAP_BLOCKS_PER_SM")) { int v = atoi (e); if (v >= 1 && v <= 4) per_sm = v; }   // tuning knob
+  // blocks per SM and frame: 1 is best for a batch (sweep in profiles/: 20.2k fps at 8K; more resident warps only spread
+  // the gathers); a single frame needs 8 to fill the SMs, as in b200vf_remap (0.29 -> of the HBM peak otherwise)
+  int per_sm = nframes >= 8 ? 1 : nframes >= 4 ? 2 : 8;
+  if (const char *e = getenv ("B200VF_REMAP_BLOCKS_PER_SM")) { int v = atoi (e); if (v >= 1 && v <= 16) per_sm = v; }   // tuning knob
   int gx = ctx->sm_count * per_sm;
   const size_t need = (L.n_chunks + 255) / 256;                           // 8 warps x 32 chunks per block and iteration
   if (need < (size_t) gx) gx = (int) need;

@@ -28,7 +28,7 @@ def draws(seed, frame, npx):
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         z = z ^ (z >> np.uint64(31))
     angle = (z >> np.uint64(56)).astype(np.int64)
-    distance = ((z >> np.uint64(3)) & np.uint64((1 << 53) - 1)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    distance = ((z >> np.uint64(4)) & np.uint64((1 << 52) - 1)).astype(np.float64) * (1.0 / 4503599627370496.0)
     return angle, distance
 
 
