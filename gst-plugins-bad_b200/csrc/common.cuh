@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include "../../include/b200vf.h"
 
@@ -26,6 +27,49 @@ struct b200vf_ctx {
   // host <-> device transfers made by b200vf_memory (map / unmap): what a pipeline of elements that keeps its frames
   // in HBM is judged by
   std::atomic<uint64_t> h2d_count{0}, h2d_bytes{0}, d2h_count{0}, d2h_bytes{0};
+  // side stream for small kernels that are independent of an op's main kernel (B200vfAux): created on first use
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+  std::mutex aux_lock;
+};
+
+// Fork / join of the context's side stream around an op's main kernel: work enqueued on stream() between construction
+// and join() starts after everything that precedes the op on `s` and is waited for by everything that follows it, but
+// is not ordered against what the op itself enqueues on `s` - a few small independent kernels fill the SMs that the
+// main kernel's last CTAs leave idle instead of adding their launch gaps and tails to the op. The lock is held from
+// fork to join: the two events are per context and ops run on several threads.
+struct B200vfAux {
+  b200vf_ctx *ctx;
+  cudaStream_t s;
+  bool active = false;
+  B200vfAux (b200vf_ctx *c, cudaStream_t main_stream, bool want) : ctx (c), s (main_stream) {
+    if (!want) return;
+    ctx->aux_lock.lock ();
+    if (!ctx->aux_stream) {
+      if (cudaStreamCreateWithFlags (&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags (&ctx->aux_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags (&ctx->aux_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError ();
+        ctx->aux_lock.unlock ();
+        return;                                                   // no side stream: everything stays on `s`
+      }
+    }
+    if (cudaEventRecord (ctx->aux_fork, s) != cudaSuccess || cudaStreamWaitEvent (ctx->aux_stream, ctx->aux_fork, 0) != cudaSuccess) {
+      cudaGetLastError ();
+      ctx->aux_lock.unlock ();
+      return;
+    }
+    active = true;
+  }
+  cudaStream_t stream () const { return active ? ctx->aux_stream : s; }
+  void join () {
+    if (!active) return;
+    cudaEventRecord (ctx->aux_join, ctx->aux_stream);
+    cudaStreamWaitEvent (s, ctx->aux_join, 0);
+    active = false;
+    ctx->aux_lock.unlock ();
+  }
+  ~B200vfAux () { join (); }
 };
 
 void b200vf_set_error (const char *fmt, ...);

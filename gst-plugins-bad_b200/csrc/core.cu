@@ -104,6 +104,9 @@ B200VF_API void b200vf_ctx_destroy (b200vf_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice (ctx->device);
   if (ctx->stream) cudaStreamDestroy (ctx->stream);
+  if (ctx->aux_stream) cudaStreamDestroy (ctx->aux_stream);
+  if (ctx->aux_fork) cudaEventDestroy (ctx->aux_fork);
+  if (ctx->aux_join) cudaEventDestroy (ctx->aux_join);
   if (ctx->tile_counters) cudaFree (ctx->tile_counters);
   if (ctx->scratch_pool) cudaMemPoolDestroy (ctx->scratch_pool);
   delete ctx;
