@@ -263,16 +263,17 @@ def test_stream_kernel_is_taken_and_padded_windows_agree(ctx, vf, orc, rng, monk
     assert np.array_equal(got, want), ("general kernel", np.argwhere(got != want)[:6])
 
 
-@pytest.mark.parametrize("sigma,c", [(1.0, 3), (1.2, 4), (2.0, 5), (2.3, 6), (3.0, 8), (3.9, 10), (5.0, 13)])
+@pytest.mark.parametrize("sigma,c", [(0.5, 2), (1.0, 3), (1.2, 4), (2.0, 5), (2.3, 6), (2.7, 7), (3.0, 8), (3.5, 9), (3.9, 10), (4.3, 11),
+                                     (4.7, 12), (5.0, 13)])
 def test_every_instantiated_half_window_of_the_stream_kernel(ctx, vf, orc, rng, monkeypatch, sigma, c):
-    """the streaming kernel exists for half-windows 4, 5, 6, 8, 10 and 13; a window runs in the first one that holds it
+    """the streaming kernel exists for every half-window from 3 to 13; a window runs in the first one that holds it
     (zero taps in front) - and must give the oracle's bytes in every larger one too"""
     w, h = 260, 70
     fr = frames.random_u8(rng, h, 4 * w)
     k, ks = vf.gauss_kernel(sigma)
     assert len(k) == 2 * c + 1                          # center = ceil (2.5 * (gfloat) sigma), gstgaussblur.c:369
     want = orc.gaussblur(fr, w, h, sigma, 1)
-    for C in (4, 5, 6, 8, 10, 13):
+    for C in range(3, 14):
         if C < c:
             continue
         monkeypatch.setenv("B200VF_GAUSS_STREAM_C", str(C))

@@ -31,7 +31,8 @@ def timeit(fn, iters=5):
 cases = [(3840, 2160, 5.0, 1, 1), (3840, 2160, 5.0, 1, 2), (3840, 2160, 5.0, 1, 8), (3840, 2160, 5.0, 1, 16), (3840, 2160, 5.0, 1, 32),
          (3840, 2160, 5.0, 0, 16), (7680, 4320, 5.0, 1, 1), (7680, 4320, 5.0, 1, 8),
          (3840, 2160, 5.0, 1, 4), (3840, 2160, 5.0, 2, 4), (3840, 2160, 5.0, 0, 4), (3840, 2160, 5.0, 1, 1), (7680, 4320, 5.0, 1, 4),
-         (3840, 2160, 1.2, 1, 4), (3840, 2160, 2.0, 1, 4), (3840, 2160, 3.3, 1, 4), (1920, 1080, 5.0, 1, 1)]
+         (3840, 2160, 1.0, 1, 4), (3840, 2160, 1.2, 1, 4), (3840, 2160, 2.0, 1, 4), (3840, 2160, 2.7, 1, 4), (3840, 2160, 3.3, 1, 4),
+         (3840, 2160, 4.3, 1, 4), (1920, 1080, 5.0, 1, 1)]
 for (w, h, sigma, p0, n) in cases:
     k, ks = b200vf.gauss_kernel(sigma)
     a = torch.randint(0, 256, (n, h, 4 * w), dtype=torch.uint8, device="cuda")
