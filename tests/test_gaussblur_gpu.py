@@ -317,3 +317,40 @@ def test_stream_kernel_edges_and_shards(ctx, vf, orc, rng, monkeypatch, p0, w, h
             ctx.gaussblur(d_one.ptr + row0 * stride, d_out.ptr + row0 * stride, w, rows, stride, p0, k, ks, row0=row0, rows=rows, full_height=h)
         got = ctx.download(d_out, one.size).reshape(h, stride)
         assert np.array_equal(got[:, :4 * w + min(pad, p0)], want[:, :4 * w + min(pad, p0)]), ("shards", sigma, np.argwhere(got != want)[:6])
+
+
+def test_two_threads_blur_on_one_context(ctx, vf, orc, rng, monkeypatch):
+    """ops are callable from any thread: two streaming threads blur byte-shifted frames on the same context, each on its
+    own stream - the side-stream fork / join around the streaming kernel (edge columns, gap bytes) uses per-context
+    events under a lock and must not cross the two calls' dependencies"""
+    import threading
+    import torch
+    monkeypatch.setenv("B200VF_GAUSS_STREAM_C", "13")
+    w, h, n = 384, 96, 6
+    k, ks = vf.gauss_kernel(5.0)
+    jobs = []
+    for t in range(2):
+        fr = [frames.random_u8(rng, h, 4 * w) for _ in range(n)]
+        jobs.append({"frames": fr, "want": [orc.gaussblur(f, w, h, 5.0, 1) for f in fr], "got": [], "err": None,
+                     "stream": torch.cuda.Stream()})
+
+    def work(job):
+        try:
+            st = job["stream"].cuda_stream
+            src = [ctx.upload(f) for f in job["frames"]]
+            dst = [ctx.alloc(f.size + 64) for f in job["frames"]]
+            for rep in range(3):
+                for s, d in zip(src, dst):
+                    ctx.gaussblur(s, d, w, h, 4 * w, 1, k, ks, stream=st)
+            job["stream"].synchronize()
+            job["got"] = [ctx.download(d, f.size).reshape(f.shape) for d, f in zip(dst, job["frames"])]
+        except Exception as e:                                  # surfaced in the main thread
+            job["err"] = e
+
+    threads = [threading.Thread(target=work, args=(j,)) for j in jobs]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for j in jobs:
+        assert j["err"] is None, j["err"]
+        for got, want in zip(j["got"], j["want"]):
+            assert np.array_equal(got, want)
