@@ -315,7 +315,11 @@ coloreffects3_kernel (uint8_t *data, int width, int height, int row_stride, size
 // ----------------------------------------------------------------- chromahold
 // gst/coloreffects/gstchromahold.c:271-360. Table: w[C] = floor(2^32/C)+1 (C >= 2):
 // |256*60*d + C/2| < 2^22 and C <= 255, so multiply-high gives the exact quotient.
-struct ChromaParams { Table256 t; int sr, sg, sb; int h1; int tolerance; uint32_t keep_mask; };
+struct ChromaParams {
+  Table256 t; int sr, sg, sb; int h1; int tolerance; uint32_t keep_mask;
+  uint32_t rep;            // 1 at the bit positions of the three channels: grey * rep replicates the grey level into them
+  uint32_t w_lo, w_hi;     // grey weights of the bytes (0, 1) and (2, 3) of a pixel word as 16-bit pairs (0 for the x / alpha byte)
+};
 
 __device__ __forceinline__ int ch_div (int num, int C, const uint32_t *tl) {
   uint32_t a = (uint32_t) abs (num);
@@ -343,8 +347,10 @@ __device__ __forceinline__ uint32_t ch_px (const uint32_t *tl, uint32_t in, cons
   if (d2 < 0) d2 += 360;
   int diff = min (d1, d2);
   if (p.h1 == -1 || diff > p.tolerance) {
-    uint32_t grey = (uint32_t) clamp255 ((13938 * r + 46869 * g + 4730 * b) >> 16);
-    return (in & p.keep_mask) | (grey << p.sr) | (grey << p.sg) | (grey << p.sb);
+    // (13938 r + 46869 g + 4730 b) >> 16 (:345-347) by two 16 x 8-bit dot products on the word itself; the weights sum
+    // to 65537, so the result is at most 255 * 65537 >> 16 = 255 and the reference's CLAMP never acts
+    const uint32_t grey = __dp2a_hi (p.w_hi, in, __dp2a_lo (p.w_lo, in, 0u)) >> 16;
+    return (in & p.keep_mask) + grey * p.rep;
   }
   return in;
 }
@@ -617,6 +623,13 @@ B200VF_API int b200vf_chromahold (b200vf_ctx *ctx, uint8_t *d_data, int width, i
   ChromaParams p;
   p.sr = shift_of (off_r); p.sg = shift_of (off_g); p.sb = shift_of (off_b);
   p.keep_mask = ~((0xffu << p.sr) | (0xffu << p.sg) | (0xffu << p.sb));
+  p.rep = (1u << p.sr) | (1u << p.sg) | (1u << p.sb);
+  {
+    uint32_t wb[4] = { 0, 0, 0, 0 };                    // weight of byte i of the pixel word
+    wb[p.sr / 8] = 13938; wb[p.sg / 8] = 46869; wb[p.sb / 8] = 4730;
+    p.w_lo = wb[0] | (wb[1] << 16);
+    p.w_hi = wb[2] | (wb[3] << 16);
+  }
   p.tolerance = tolerance;
   {   // rgb_to_hue of the target on the host (init_params, gstchromahold.c:362-366)
     int r = target_r, g = target_g, b = target_b;

@@ -14,10 +14,10 @@ __device__ __forceinline__ int d2i (double x) {
   if (!(fabs (x) < 2147483648.0)) return (int) 0x80000000;      // NaN too; (-2^31 - 1, -2^31] truncates to INT_MIN anyway
   const double M = 6755399441055744.0;
   const double t = x + M;
-  int r = __double2loint (t);
+  unsigned int r = (unsigned int) __double2loint (t);            // unsigned: 2^31 - 0.5 rounds to 2^31 first, then steps back
   const double rn = t - M;
   if (x >= 0) { if (rn > x) r--; } else { if (rn < x) r++; }
-  return r;
+  return (int) r;
 }
 // geometricmath.c:171-180
 __device__ __forceinline__ double mod_float (double a, double b) {

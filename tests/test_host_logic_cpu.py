@@ -348,3 +348,37 @@ def test_smooth_division_trick_is_exact():
             r = (rcp.view(np.uint32) + np.uint32(ulps & 0xffffffff)).view(np.float32) if ulps else rcp
             got = ((total.astype(np.float32) + np.float32(0.5)) * r).astype(np.int64)
             assert np.array_equal(got, total // num), (num, ulps)
+
+
+def test_fp64_adder_truncation_trick_is_cvttsd2si():
+    """csrc/gt_resolve.cuh converts double -> int without F2I: t = x + 1.5 * 2^52 rounds x to the nearest integer (ties to
+    even) and leaves it in the low word; one compare against t - 1.5 * 2^52 turns nearest into toward-zero. Restated in
+    numpy (IEEE doubles, round-to-nearest-even like the GPU's DADD) and compared with C's (int) on ties, neighbours of
+    integers, negatives, the int32 borders, NaN and infinities."""
+    M = np.float64(6755399441055744.0)
+
+    def d2i(x):
+        x = np.asarray(x, np.float64)
+        with np.errstate(invalid="ignore"):
+            inrange = np.abs(x) < 2147483648.0
+            xs = np.where(inrange, x, 0.0)
+            t = xs + M
+            r = (t.view(np.uint64) & np.uint64(0xffffffff)).astype(np.uint32)
+            rn = t - M
+            r = np.where((xs >= 0) & (rn > xs), r - np.uint32(1), r)        # uint32 arithmetic wraps, as on the device
+            r = np.where((xs < 0) & (rn < xs), r + np.uint32(1), r)
+        return np.where(inrange, r.astype(np.uint32).view(np.int32).astype(np.int64), -2147483648)
+
+    rng = np.random.default_rng(3)
+    ints = rng.integers(-2**31 + 2, 2**31 - 2, 4000).astype(np.float64)
+    cases = [ints, ints + 0.5, ints - 0.5, np.nextafter(ints, np.inf), np.nextafter(ints, -np.inf),
+             rng.uniform(-1e4, 1e4, 20000), rng.uniform(-2.2e9, 2.2e9, 20000),
+             np.array([0.0, -0.0, 0.5, -0.5, 1.5, -1.5, 2.5, -2.5, 0.9999999999999999, -0.9999999999999999, 2147483647.0,
+                       2147483647.5, 2147483648.0, -2147483648.0, -2147483648.5, -2147483649.0, 1e300, -1e300, np.inf, -np.inf,
+                       np.nan, 5e-324, -5e-324])]
+    x = np.concatenate(cases)
+    with np.errstate(invalid="ignore"):
+        ok = np.abs(x) < 2147483649.0
+        want = np.where(ok & (np.trunc(np.where(ok, x, 0)) >= -2147483648.0) & (np.trunc(np.where(ok, x, 0)) <= 2147483647.0),
+                        np.trunc(np.where(ok, x, 0)), -2147483648.0).astype(np.int64)
+    assert np.array_equal(d2i(x), want), x[d2i(x) != want][:10]
