@@ -319,15 +319,19 @@ struct ChromaParams {
   Table256 t; int sr, sg, sb; int h1; int tolerance; uint32_t keep_mask;
   uint32_t rep;            // 1 at the bit positions of the three channels: grey * rep replicates the grey level into them
   uint32_t w_lo, w_hi;     // grey weights of the bytes (0, 1) and (2, 3) of a pixel word as 16-bit pairs (0 for the x / alpha byte)
+  int branchy;             // A/B knob: the literal control flow instead of selects
+  uint32_t sel_r, sel_g, sel_b;   // PRMT selectors: channel byte, zero-extended
+  int tol_eff;             // tolerance, or -1 when h1 == -1 (every pixel goes grey)
 };
 
+// The literal control flow of rgb_to_hue / hue_dist / the process loop (A/B knob B200VF_CHROMA_BRANCHY=1): shorter per
+// path, but every data-dependent branch splits the warp on frames without spatial coherence.
 __device__ __forceinline__ int ch_div (int num, int C, const uint32_t *tl) {
   uint32_t a = (uint32_t) abs (num);
   uint32_t q = (C == 1) ? a : __umulhi (a, tl[C << 5]);
   return num < 0 ? -(int) q : (int) q;                     // C division truncates toward zero
 }
-
-__device__ __forceinline__ int ch_hue (int r, int g, int b, const uint32_t *tl) {
+__device__ __forceinline__ int ch_hue_branchy (int r, int g, int b, const uint32_t *tl) {
   int m = min (min (r, g), b), M = max (max (r, g), b);
   int C = M - m, C2 = C >> 1, h;
   if (C == 0) return -1;                                   // G_MAXUINT as gint (:282)
@@ -338,27 +342,61 @@ __device__ __forceinline__ int ch_hue (int r, int g, int b, const uint32_t *tl) 
   if (h >= 360) h -= 360; else if (h < 0) h += 360;
   return h;
 }
-
-__device__ __forceinline__ uint32_t ch_px (const uint32_t *tl, uint32_t in, const ChromaParams &p) {
+__device__ __forceinline__ uint32_t ch_px_branchy (const uint32_t *tl, uint32_t in, const ChromaParams &p) {
   int r = (in >> p.sr) & 0xff, g = (in >> p.sg) & 0xff, b = (in >> p.sb) & 0xff;
-  int h2 = ch_hue (r, g, b, tl);
+  int h2 = ch_hue_branchy (r, g, b, tl);
   int d1 = p.h1 - h2, d2 = h2 - p.h1;
   if (d1 < 0) d1 += 360;
   if (d2 < 0) d2 += 360;
   int diff = min (d1, d2);
   if (p.h1 == -1 || diff > p.tolerance) {
-    // (13938 r + 46869 g + 4730 b) >> 16 (:345-347) by two 16 x 8-bit dot products on the word itself; the weights sum
-    // to 65537, so the result is at most 255 * 65537 >> 16 = 255 and the reference's CLAMP never acts
     const uint32_t grey = __dp2a_hi (p.w_hi, in, __dp2a_lo (p.w_lo, in, 0u)) >> 16;
     return (in & p.keep_mask) + grey * p.rep;
   }
   return in;
 }
 
+// Branch-free: the three hue sectors, the grey pixels (C == 0) and the hold / grey decision depend on the data, and on
+// random frames every warp diverged at each of them (BSSY / BSYNC around every branch: 4 per pixel in the SASS); selects
+// cost a few instructions more per path and far fewer per warp.
+__device__ __forceinline__ int ch_hue (int r, int g, int b, const uint32_t *tl) {
+  const int m = min (min (r, g), b), M = max (max (r, g), b);
+  const int C = M - m;
+  const bool ir = (M == r), ig = (M == g);
+  const int x = ir ? g : (ig ? b : r), y = ir ? b : (ig ? r : g);
+  const int off = ir ? 0 : (ig ? 120 * 256 : 240 * 256);
+  const int num = 256 * 60 * (x - y) + (C >> 1);
+  const uint32_t a = (uint32_t) abs (num);
+  uint32_t q = __umulhi (a, tl[C << 5]);                   // exact quotient for C >= 2 (table comment above)
+  q = (C == 1) ? a : q;
+  int h = ((num < 0) ? -(int) q : (int) q) + off;          // C division truncates toward zero
+  h >>= 8;
+  h = (h >= 360) ? h - 360 : ((h < 0) ? h + 360 : h);
+  return (C == 0) ? -1 : h;                                // G_MAXUINT as gint (:282)
+}
+
+__device__ __forceinline__ uint32_t ch_px (const uint32_t *tl, uint32_t in, const ChromaParams &p) {
+  // channel bytes by PRMT (one ALU instruction each; shift + mask are two, and the ALU pipe - half rate - is what
+  // bounds this kernel: ~30 ALU instructions per pixel)
+  const int r = (int) __byte_perm (in, 0u, p.sel_r), g = (int) __byte_perm (in, 0u, p.sel_g), b = (int) __byte_perm (in, 0u, p.sel_b);
+  const int h2 = ch_hue (r, g, b, tl);
+  // hue_dist (:301-315): d1 = h1 - h2, d2 = h2 - h1, each + 360 when negative, the smaller one. With |d| <= 360 that is
+  // min (|d|, 360 - |d|) - also for h2 = -1 (grey pixel): min (h1 + 1, 359 - h1).
+  const int ad = abs (p.h1 - h2);
+  const int diff = min (ad, 360 - ad);
+  // (13938 r + 46869 g + 4730 b) >> 16 (:345-347) by two 16 x 8-bit dot products on the word itself; the weights sum
+  // to 65537, so the result is at most 255 * 65537 >> 16 = 255 and the reference's CLAMP never acts
+  const uint32_t grey = __dp2a_hi (p.w_hi, in, __dp2a_lo (p.w_lo, in, 0u)) >> 16;
+  const uint32_t greyed = (in & p.keep_mask) + grey * p.rep;
+  return (diff > p.tol_eff) ? greyed : in;                 // tol_eff = -1 when the target itself is grey (h1 == -1: always)
+}
+
 struct ChromaOp {                        // stream.cuh operator
   ChromaParams p;
   __device__ __forceinline__ void fill (uint32_t *tab) const { table_fill (tab, p.t); }
-  __device__ __forceinline__ uint32_t apply (const uint32_t *tl, uint32_t px) const { return ch_px (tl, px, p); }
+  __device__ __forceinline__ uint32_t apply (const uint32_t *tl, uint32_t px) const {
+    return p.branchy ? ch_px_branchy (tl, px, p) : ch_px (tl, px, p);
+  }
 };
 
 __global__ void __launch_bounds__ (256)
@@ -631,6 +669,8 @@ B200VF_API int b200vf_chromahold (b200vf_ctx *ctx, uint8_t *d_data, int width, i
     p.w_hi = wb[2] | (wb[3] << 16);
   }
   p.tolerance = tolerance;
+  p.branchy = getenv ("B200VF_CHROMA_BRANCHY") ? 1 : 0;
+  p.sel_r = 0x4440u | (unsigned) (p.sr / 8); p.sel_g = 0x4440u | (unsigned) (p.sg / 8); p.sel_b = 0x4440u | (unsigned) (p.sb / 8);
   {   // rgb_to_hue of the target on the host (init_params, gstchromahold.c:362-366)
     int r = target_r, g = target_g, b = target_b;
     int m = r < g ? r : g; if (b < m) m = b;
@@ -646,6 +686,7 @@ B200VF_API int b200vf_chromahold (b200vf_ctx *ctx, uint8_t *d_data, int width, i
     }
     p.h1 = h;
   }
+  p.tol_eff = (p.h1 == -1) ? -1 : tolerance;
   p.t.w[0] = p.t.w[1] = 0;
   for (int c = 2; c < 256; c++) p.t.w[c] = (uint32_t) (0x100000000ull / (uint64_t) c) + 1u;
   size_t nbytes;
