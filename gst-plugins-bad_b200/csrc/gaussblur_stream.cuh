@@ -32,7 +32,7 @@
 // b200vf_gauss_selftest_div1. Truncated windows at the frame edges use div2 (reciprocal + two corrections).
 //
 // Byte-shifted frames (AYUV ...) are blurred as ALIGNED words as in gaussblur_kernel<.., 0> (p0v, patch_w); the two
-// pixel columns that straddle the frame edge there (pixel 0, pixel w-1) are written by gauss_lastcol_* (gaussblur.cu).
+// pixel columns that straddle the frame edge there (pixel 0, pixel w-1) are written by gauss_lastcol_kernel (gaussblur.cu).
 //
 // What the ncu captures taught (profiles/r02_gaussblur_stream.md):
 //  * every role's hot loop is ~30 KB of straight-line code; the SM's instruction caches hold two such streams, not
@@ -327,7 +327,7 @@ gaussblur_stream_kernel (const __grid_constant__ CUtensorMap src_map, const __gr
     // This thread's two bytes (2 * pair, 2 * pair + 1 of aligned column xg) are stored when the column lies in the launch's
     // region and both bytes belong to a pixel of the frame: byte i is pixel xg's (i >= p0v) or pixel xg - 1's (i < p0v).
     // Columns 0 and w of a byte-shifted image hold bytes of one pixel only: those two pixel columns are written by
-    // gauss_lastcol_* (gaussblur.cu), not here.
+    // gauss_lastcol_kernel (gaussblur.cu), not here.
     const int pair = tv & 1;
     bool store = xg >= p.x_begin && xg < p.x_end;
     for (int i = 2 * pair; i < 2 * pair + 2; i++) store = store && (i >= p0v ? (xg >= 0 && xg < p.w) : (xg >= 1 && xg <= p.w));

@@ -286,7 +286,7 @@ def test_every_instantiated_half_window_of_the_stream_kernel(ctx, vf, orc, rng, 
 @pytest.mark.parametrize("w,h,pad", [(256, 100, 0), (257, 70, 12), (384, 64, 0), (131, 40, 4), (640, 33, 0)])
 def test_stream_kernel_edges_and_shards(ctx, vf, orc, rng, monkeypatch, p0, w, h, pad):
     """the streaming kernel on small frames (size threshold lifted): widths that are multiples of the 128-column strip
-    (aligned column w would be a strip of its own: the edge pixel columns come from gauss_lastcol_*), ragged widths,
+    (aligned column w would be a strip of its own: the edge pixel columns come from gauss_lastcol_kernel), ragged widths,
     padded rows, few CTAs (ranges spanning strips and frames), and row shards against the whole-frame oracle"""
     if (4 * w + pad) % 16:
         pytest.skip("rows not 16-byte aligned: pre-pass route, general kernel")
