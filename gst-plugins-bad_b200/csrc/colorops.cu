@@ -359,34 +359,36 @@ __device__ __forceinline__ uint32_t ch_px_branchy (const uint32_t *tl, uint32_t 
 // Branch-free: the three hue sectors, the grey pixels (C == 0) and the hold / grey decision depend on the data, and on
 // random frames every warp diverged at each of them (BSSY / BSYNC around every branch: 4 per pixel in the SASS); selects
 // cost a few instructions more per path and far fewer per warp.
+// Returns the hue WITHOUT the reference's wrap into [0, 360) (:292-296): -60 .. 299, or -1 for grey pixels. The only
+// consumer is the circular distance below, which does not care (checked over all 2^24 colours: tools note in
+// profiles/r02_chromahold.md). The three right shifts go through multiply-high: the ALU pipe (half rate) bounds this
+// kernel, the FMA pipe has room.
 __device__ __forceinline__ int ch_hue (int r, int g, int b, const uint32_t *tl) {
   const int m = min (min (r, g), b), M = max (max (r, g), b);
   const int C = M - m;
   const bool ir = (M == r), ig = (M == g);
   const int x = ir ? g : (ig ? b : r), y = ir ? b : (ig ? r : g);
   const int off = ir ? 0 : (ig ? 120 * 256 : 240 * 256);
-  const int num = 256 * 60 * (x - y) + (C >> 1);
+  const int num = 256 * 60 * (x - y) + (int) __umulhi ((uint32_t) C, 0x80000000u);      // + (C >> 1)
   const uint32_t a = (uint32_t) abs (num);
   uint32_t q = __umulhi (a, tl[C << 5]);                   // exact quotient for C >= 2 (table comment above)
   q = (C == 1) ? a : q;
-  int h = ((num < 0) ? -(int) q : (int) q) + off;          // C division truncates toward zero
-  h >>= 8;
-  h = (h >= 360) ? h - 360 : ((h < 0) ? h + 360 : h);
-  return (C == 0) ? -1 : h;                                // G_MAXUINT as gint (:282)
+  const int h = ((num < 0) ? -(int) q : (int) q) + off;    // C division truncates toward zero
+  return (C == 0) ? -1 : __mulhi (h, 1 << 24);             // h >> 8 (arithmetic); G_MAXUINT as gint for greys (:282)
 }
 
 __device__ __forceinline__ uint32_t ch_px (const uint32_t *tl, uint32_t in, const ChromaParams &p) {
-  // channel bytes by PRMT (one ALU instruction each; shift + mask are two, and the ALU pipe - half rate - is what
-  // bounds this kernel: ~30 ALU instructions per pixel)
+  // channel bytes by PRMT (one ALU instruction each; shift + mask are two)
   const int r = (int) __byte_perm (in, 0u, p.sel_r), g = (int) __byte_perm (in, 0u, p.sel_g), b = (int) __byte_perm (in, 0u, p.sel_b);
   const int h2 = ch_hue (r, g, b, tl);
-  // hue_dist (:301-315): d1 = h1 - h2, d2 = h2 - h1, each + 360 when negative, the smaller one. With |d| <= 360 that is
-  // min (|d|, 360 - |d|) - also for h2 = -1 (grey pixel): min (h1 + 1, 359 - h1).
-  const int ad = abs (p.h1 - h2);
-  const int diff = min (ad, 360 - ad);
+  // hue_dist (:301-315) = the circular distance of the two hues: d1 = h1 - h2, d2 = h2 - h1, each + 360 when negative,
+  // the smaller one. With a = |h1 - h2| and h2 possibly unwrapped (a <= 420) that is min (a, |360 - a|) - also for
+  // h2 = -1 (grey pixel): min (h1 + 1, 359 - h1).
+  const int a = abs (p.h1 - h2);
+  const int diff = min (a, abs (360 - a));
   // (13938 r + 46869 g + 4730 b) >> 16 (:345-347) by two 16 x 8-bit dot products on the word itself; the weights sum
   // to 65537, so the result is at most 255 * 65537 >> 16 = 255 and the reference's CLAMP never acts
-  const uint32_t grey = __dp2a_hi (p.w_hi, in, __dp2a_lo (p.w_lo, in, 0u)) >> 16;
+  const uint32_t grey = __umulhi (__dp2a_hi (p.w_hi, in, __dp2a_lo (p.w_lo, in, 0u)), 65536u);
   const uint32_t greyed = (in & p.keep_mask) + grey * p.rep;
   return (diff > p.tol_eff) ? greyed : in;                 // tol_eff = -1 when the target itself is grey (h1 == -1: always)
 }
