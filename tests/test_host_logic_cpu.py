@@ -382,3 +382,22 @@ def test_fp64_adder_truncation_trick_is_cvttsd2si():
         want = np.where(ok & (np.trunc(np.where(ok, x, 0)) >= -2147483648.0) & (np.trunc(np.where(ok, x, 0)) <= 2147483647.0),
                         np.trunc(np.where(ok, x, 0)), -2147483648.0).astype(np.int64)
     assert np.array_equal(d2i(x), want), x[d2i(x) != want][:10]
+
+
+def test_host_builders_dense_sweeps(vf, orc):
+    """the host-side builders against the reference's own C over dense parameter sweeps: chromium's cos-table LUT for
+    every fourth (edge-a, edge-b) pair plus the borders, solarize for 4000 random (threshold, start, end) triples
+    incl. start > end, gaussian taps and prefix sums for 1500 random sigmas (bit-equal floats)"""
+    rng = np.random.default_rng(11)
+    allb = px_all()
+    edges = sorted(set(range(0, 257, 4)) | {1, 255, 256})
+    for a in edges:
+        for b in (0, 1, 2, 127, 128, 255, 256, int(rng.integers(0, 257))):
+            assert np.array_equal(apply_lut(vf.lut_chromium(a, b), allb), orc.chromium(allb, a, b)), (a, b)
+    for t, s, e in rng.integers(0, 257, (4000, 3)):
+        assert np.array_equal(apply_lut(vf.lut_solarize(int(t), int(s), int(e)), allb), orc.solarize(allb, int(t), int(s), int(e))), (t, s, e)
+    for s in np.concatenate([rng.uniform(-20, 20, 1200), rng.uniform(-1.5, 1.5, 300)]):
+        s = float(np.float32(s))
+        k, ks = vf.gauss_kernel(s)
+        rk, rks = orc.gauss_kernel(s)
+        assert np.array_equal(k.view(np.uint32), rk.view(np.uint32)) and np.array_equal(ks.view(np.uint32), rks.view(np.uint32)), s
