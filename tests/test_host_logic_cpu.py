@@ -401,3 +401,31 @@ def test_host_builders_dense_sweeps(vf, orc):
         k, ks = vf.gauss_kernel(s)
         rk, rks = orc.gauss_kernel(s)
         assert np.array_equal(k.view(np.uint32), rk.view(np.uint32)) and np.array_equal(ks.view(np.uint32), rks.view(np.uint32)), s
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="needs oracle/_ref")
+def test_geometric_maps_match_reference_over_random_properties(vf):
+    """every deterministic map function against the reference's own *_map (compiled from /root/reference) for seeded
+    random properties over their ranges, at a size whose centre is not a pixel: the double maps must be bit-equal"""
+    R = oracle.get("reference")
+    rng = np.random.default_rng(5)
+    w, h = 93, 61
+    circle = {"x_center": (0, 1), "y_center": (0, 1), "radius": (0, 1)}
+    ranges = {
+        "fisheye": {}, "tunnel": dict(circle), "mirror": {"mode": (0, 4)},
+        "bulge": dict(circle, zoom=(1, 20)), "stretch": dict(circle, intensity=(0, 1)),
+        "square": {"width": (0, 1), "height": (0, 1), "zoom": (1, 20)},
+        "circle": dict(circle, angle=(-3.2, 3.2), spread_angle=(0.2, 6.3), height=(1, 80)),
+        "kaleidoscope": dict(circle, angle=(-3.2, 3.2), angle2=(-3.2, 3.2), sides=(2, 9)),
+        "pinch": dict(circle, intensity=(-1, 1)), "rotate": {"angle": (-6.3, 6.3)},
+        "sphere": dict(circle, refraction=(0.3, 3.0)), "twirl": dict(circle, angle=(-6.3, 6.3)),
+        "waterripple": dict(circle, amplitude=(-40, 40), phase=(-7, 7), wavelength=(2, 60)),
+        "perspective": {"matrix_%d" % i: (-2, 2) for i in range(9)},
+    }
+    for el, rr in ranges.items():
+        for trial in range(5):
+            props = {k: (float(np.floor(rng.uniform(*v))) if k in ("sides", "height", "mode") and el in ("kaleidoscope", "circle", "mirror")
+                         else float(rng.uniform(*v))) for k, v in rr.items()}
+            m = vf.gt_build_map(el, w, h, props)
+            r = R.gt_map(el, w, h, refprops.full(el, props))
+            assert ((m.view(np.uint64) == r.view(np.uint64)) | (np.isnan(m) & np.isnan(r))).all(), (el, props)
