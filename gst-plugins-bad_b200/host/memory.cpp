@@ -19,6 +19,23 @@ void drop_pending (b200vf_memory *m) {
   if (src) b200vf_memory_unref (src);
 }
 
+// A memory remembers the stream that used it last. When another stream is about to touch it, that stream is ordered
+// after the last use (GstCudaMemory assumes one stream per context and synchronises; elements of one pipeline
+// normally share the context's stream here too, so this is the uncommon path): caller holds m->mu.
+int order_after_last_use (b200vf_memory *m, cudaStream_t s) {
+  if (!m->busy || m->last_stream == s) return B200VF_OK;
+  cudaEvent_t ev = nullptr;
+  B200VF_CHECK_CUDA (cudaEventCreateWithFlags (&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord (ev, m->last_stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent (s, ev, 0);
+  cudaEventDestroy (ev);                                   // (released once the record has completed)
+  if (e != cudaSuccess) {
+    b200vf_set_error ("memory: ordering two streams failed: %s", cudaGetErrorString (e));
+    return B200VF_E_CUDA;
+  }
+  return B200VF_OK;
+}
+
 // launch the pending chain of m into m->d (caller holds m->mu)
 int flush_pending (b200vf_memory *m, cudaStream_t s) {
   b200vf_pending *pc = m->pending;
@@ -59,7 +76,8 @@ int upload_if_needed (b200vf_memory *m, cudaStream_t s) {
 int b200vf_memory_device_read (b200vf_memory *m, cudaStream_t s, const uint8_t **d_out) {
   B200VF_REQUIRE (m && d_out, B200VF_E_INVAL, "memory: NULL argument");
   std::lock_guard<std::mutex> g (m->mu);
-  int rc = flush_pending (m, s);
+  int rc = order_after_last_use (m, s);
+  if (!rc) rc = flush_pending (m, s);
   if (!rc) rc = upload_if_needed (m, s);
   m->last_stream = s; m->busy = true;
   *d_out = m->d;
@@ -69,6 +87,7 @@ int b200vf_memory_device_read (b200vf_memory *m, cudaStream_t s, const uint8_t *
 int b200vf_memory_device_write (b200vf_memory *m, cudaStream_t s, uint8_t **d_out) {
   B200VF_REQUIRE (m && d_out, B200VF_E_INVAL, "memory: NULL argument");
   std::lock_guard<std::mutex> g (m->mu);
+  if (int rc = order_after_last_use (m, s)) return rc;
   drop_pending (m);                                      // whatever was recorded is overwritten before anyone saw it
   m->flags &= ~B200VF_MEMORY_NEED_UPLOAD;
   m->flags |= B200VF_MEMORY_NEED_DOWNLOAD;
@@ -80,7 +99,8 @@ int b200vf_memory_device_write (b200vf_memory *m, cudaStream_t s, uint8_t **d_ou
 int b200vf_memory_device_rw (b200vf_memory *m, cudaStream_t s, uint8_t **d_out) {
   B200VF_REQUIRE (m && d_out, B200VF_E_INVAL, "memory: NULL argument");
   std::lock_guard<std::mutex> g (m->mu);
-  int rc = flush_pending (m, s);
+  int rc = order_after_last_use (m, s);
+  if (!rc) rc = flush_pending (m, s);
   if (!rc) rc = upload_if_needed (m, s);
   m->flags |= B200VF_MEMORY_NEED_DOWNLOAD;
   m->last_stream = s; m->busy = true;
@@ -182,12 +202,13 @@ B200VF_API int b200vf_memory_map (b200vf_memory *mem, int flags, void **data, vo
     if (!(mem->flags & B200VF_MEMORY_NEED_UPLOAD) && !mem->pending) mem->flags |= B200VF_MEMORY_NEED_DOWNLOAD;
   }
   if (flags & B200VF_MAP_READ) {
-    int rc = flush_pending (mem, s);
+    int rc = order_after_last_use (mem, s);
+    if (!rc) rc = flush_pending (mem, s);
     if (rc) return rc;
     if (mem->flags & B200VF_MEMORY_NEED_DOWNLOAD) {
       B200VF_CHECK_CUDA (cudaMemcpyAsync (mem->h, mem->d, mem->bytes, cudaMemcpyDeviceToHost, s));
       B200VF_CHECK_CUDA (cudaStreamSynchronize (s));
-      if (mem->last_stream == s) mem->busy = false;
+      mem->busy = false;                                 // s was ordered after the last use and has drained
       mem->ctx->d2h_count.fetch_add (1, std::memory_order_relaxed);
       mem->ctx->d2h_bytes.fetch_add (mem->bytes, std::memory_order_relaxed);
       mem->flags &= ~B200VF_MEMORY_NEED_DOWNLOAD;
@@ -195,7 +216,9 @@ B200VF_API int b200vf_memory_map (b200vf_memory *mem, int flags, void **data, vo
   } else {
     // write-only host map: the old contents (and anything recorded) are dead
     drop_pending (mem);
+    if (mem->busy && mem->last_stream != s) B200VF_CHECK_CUDA (cudaStreamSynchronize (mem->last_stream));
     B200VF_CHECK_CUDA (cudaStreamSynchronize (s));        // device work that still reads the old bytes
+    mem->busy = false;
     mem->flags &= ~B200VF_MEMORY_NEED_DOWNLOAD;
   }
   mem->map_flags = flags; mem->map_count++;

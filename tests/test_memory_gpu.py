@@ -166,3 +166,29 @@ def test_out_of_place_elements_reject_aliased_memories(ctx, vf):
     d = ctx.alloc(64 * 16 * 4)
     with pytest.raises(vf.B200vfError):
         g.transform_device(d, d)
+
+
+def test_two_streams_are_ordered_through_the_memory(ctx, vf, orc, rng, monkeypatch):
+    """an element writes a memory on stream A (behind a long blur, so that it is still queued), another element reads it
+    on stream B straight away: the memory orders B after its last use on A (GstCudaMemory synchronises instead)"""
+    import torch
+    monkeypatch.setenv("B200VF_NO_DEFER", "1")                 # launch every element as it comes
+    w, h = 3840, 2160
+    fr = frames.random_u8(rng, h, 4 * w)
+    want = orc.dilate(orc.burn(fr.view(np.uint32), 175).reshape(h, w), False).view(np.uint8).reshape(h, 4 * w)
+    burn, dil = ctx.element("burn"), ctx.element("dilate")
+    burn.set_caps("BGRx", "BGRx", w, h); dil.set_caps("BGRx", "BGRx", w, h)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    k, ks = vf.gauss_kernel(5.0)
+    big = ctx.upload(frames.random_u8(rng, 4 * h, 4 * w))
+    big_out = ctx.alloc(4 * h * 4 * w + 64)
+    for rep in range(3):
+        m0, m1, m2 = ctx.memory(4 * w * h), ctx.memory(4 * w * h), ctx.memory(4 * w * h)
+        m0.write(fr)
+        ctx.gaussblur(big, big_out, w, h, 4 * w, 1, k, ks, nframes=4, stream=sa.cuda_stream)   # ~0.5 ms of work ahead on A
+        burn.transform_mem(m0, m1, stream=sa.cuda_stream)
+        dil.transform_mem(m1, m2, stream=sb.cuda_stream)                                           # B: no wait of its own
+        got = m2.read().reshape(h, 4 * w)
+        assert np.array_equal(got, want), rep
+        for m in (m0, m1, m2):
+            m.close()
