@@ -115,6 +115,8 @@ int b200vf_memcpy_d2h (b200vf_ctx *ctx, void *h_dst, const void *d_src, size_t b
  * element that cannot join the chain. `bayer2rgb ! coloreffects ! solarize` (BASELINE.json configs[4]) through
  * memories is 1 upload, 1 launch, 1 download. The chain holds a reference to its source memory.
  * Memories are reference counted (GstMiniObject): a pool memory returns to its pool when the last reference goes. */
+/* Streams: every map / element call names the stream it works on (NULL = the context's). A memory remembers the
+ * stream of its last device use; a different stream is ordered behind it with an event before it touches the bytes. */
 #define B200VF_MAP_READ 1
 #define B200VF_MAP_WRITE 2
 #define B200VF_MAP_DEVICE 4
